@@ -1,0 +1,1226 @@
+// oracle.cpp -- CPU restatement of the reference's per-pixel render path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing in the product (spectral_raytracer_b200/,
+// include/) may include, link or call this file; only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
+//
+// What it restates (all citations are into /root/reference/src):
+//   shader.rs:271-755   ray generation, submit_ray, intersection, hit, miss,
+//                       geometry, hammersley, pcg3d, sampling
+//   shader.rs:59-166    Ray / Aabb constructors
+//   spectrum.rs:49-122, 141-187, 215-261, 379-484, 582-594, 654-770
+//   custom_image.rs:18-22, 59-101
+//   main.rs:1280-1341   frame = one job per row, serial blend, frame ids 0..N-1
+//   main.rs:1538-1635, 1638-1758, 1970-1985  the two scene presets + camera
+//
+// The reference is Rust and cannot be built in this image (no cargo/rustc, no
+// vendored crates), so there is no oracle/_ref.  Arithmetic that lives in the
+// un-vendored dependency nalgebra 0.33.2 (Cargo.lock:2196-2198) is restated in
+// namespace na below from its published algorithm.
+//
+// PARITY PINNING: the reference's own tests pin only spectrum.rs
+// (spectrum.rs:777-869: wavelength_to_XYZ, XYZ->RGB matrix, black body) plus the
+// Hammersley doc sequence (shader.rs:667-669); tests/test_oracle_kat.py checks
+// this file against every one of them.  For shader.rs / custom_image.rs /
+// apply_shader2 the reference has no test, fixture or golden image:
+// **parity unpinned** there -- this restatement is the definition.
+//
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math (Rust never
+// contracts a*b+c into an fma and never reassociates).  All arithmetic is f32
+// except black_body_radiation (f64), like the reference.
+//
+// Cost structure is kept faithful on purpose (528-byte by-value spectra,
+// per-ray heap vector + stable sort, per-sample get_rgb_early with CIE lerps,
+// double slab test for plain boxes) because this is also the timed CPU baseline.
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <optional>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+namespace na {
+// nalgebra 0.33.2 semantics, restated (un-vendored).  normalize() divides each
+// component by sqrt(norm_squared); the 3-vector dot is (a0*b0 + a1*b1) + a2*b2;
+// matrix*vector accumulates column by column: ((m_i0*v0) + m_i1*v1) + m_i2*v2.
+struct V3 {
+    float x, y, z;
+    float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator-(V3 a) { return {-a.x, -a.y, -a.z}; }
+inline V3 operator*(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline V3 operator*(float s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline V3 operator/(V3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+inline float dot(V3 a, V3 b) {
+    float p = a.x * b.x, q = a.y * b.y, r = a.z * b.z;
+    return (p + q) + r;
+}
+inline float norm_squared(V3 a) { return dot(a, a); }
+inline float norm(V3 a) { return std::sqrt(norm_squared(a)); }
+inline V3 normalize(V3 a) { return a / norm(a); }
+inline V3 cross(V3 a, V3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// Row-major 3x3.  Rotation3 is a wrapper around this; inverse() == transpose().
+struct M3 {
+    float m[3][3];
+};
+inline V3 mul(const M3& a, V3 v) {
+    V3 r;
+    r.x = (a.m[0][0] * v.x + a.m[0][1] * v.y) + a.m[0][2] * v.z;
+    r.y = (a.m[1][0] * v.x + a.m[1][1] * v.y) + a.m[1][2] * v.z;
+    r.z = (a.m[2][0] * v.x + a.m[2][1] * v.y) + a.m[2][2] * v.z;
+    return r;
+}
+inline M3 transpose(const M3& a) {
+    M3 t;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) t.m[i][j] = a.m[j][i];
+    return t;
+}
+// Rotation3::from_euler_angles(roll, pitch, yaw) = Rz(yaw) * Ry(pitch) * Rx(roll).
+inline M3 from_euler_angles(float roll, float pitch, float yaw) {
+    float sr = std::sin(roll), cr = std::cos(roll);
+    float sp = std::sin(pitch), cp = std::cos(pitch);
+    float sy = std::sin(yaw), cy = std::cos(yaw);
+    M3 r;
+    r.m[0][0] = cy * cp;  r.m[0][1] = cy * sp * sr - sy * cr;  r.m[0][2] = cy * sp * cr + sy * sr;
+    r.m[1][0] = sy * cp;  r.m[1][1] = sy * sp * sr + cy * cr;  r.m[1][2] = sy * sp * cr - cy * sr;
+    r.m[2][0] = -sp;      r.m[2][1] = cp * sr;                 r.m[2][2] = cp * cr;
+    return r;
+}
+// Rotation3::face_towards(dir, up): columns [x y z] with z = dir.
+inline M3 face_towards(V3 dir, V3 up) {
+    V3 z = normalize(dir);
+    V3 x = normalize(cross(up, z));
+    V3 y = normalize(cross(z, x));
+    M3 r;
+    r.m[0][0] = x.x; r.m[0][1] = y.x; r.m[0][2] = z.x;
+    r.m[1][0] = x.y; r.m[1][1] = y.y; r.m[1][2] = z.y;
+    r.m[2][0] = x.z; r.m[2][1] = y.z; r.m[2][2] = z.z;
+    return r;
+}
+}  // namespace na
+
+using na::V3;
+using na::M3;
+
+namespace {
+
+// Rust's f32::max / f32::min return the non-NaN operand; so do fmaxf / fminf.
+inline float rmax(float a, float b) { return std::fmax(a, b); }
+inline float rmin(float a, float b) { return std::fmin(a, b); }
+
+constexpr float F32_DELTA = 0.00001f;                         // shader.rs:7
+constexpr float NEW_RAY_POSITION_OFFSET_DISTANCE = 0.00001f;  // shader.rs:8
+constexpr float SPECULAR_MIN_RAY_DISTANCE = 0.0001f;          // shader.rs:14
+constexpr float PI_F = 3.14159265358979323846f;               // std::f32::consts::PI
+constexpr float FRAC_PI_2_F = 1.57079632679489661923f;
+constexpr int NBR_OF_SAMPLES_MAX = 128;                       // spectrum.rs:8
+
+// ---------------------------------------------------------------- Spectrum
+// spectrum.rs:25-30.  Copy type of 528 bytes; every operator result copies all
+// 128 floats no matter what nbr_of_samples is, exactly like the reference.
+struct Spectrum {
+    size_t nbr_of_samples;
+    float intensities[NBR_OF_SAMPLES_MAX];
+    float lo, hi;  // SpectrumType::EquidistantSamples(lo, hi)
+};
+
+Spectrum new_from_list(const float* arr, float lo, float hi, size_t n) {  // spectrum.rs:62-68
+    Spectrum s;
+    s.nbr_of_samples = n;
+    std::memcpy(s.intensities, arr, sizeof(s.intensities));
+    s.lo = lo;
+    s.hi = hi;
+    return s;
+}
+Spectrum new_singular_reflectance_factor(float lo, float hi, size_t n, float f) {  // :100-106
+    float arr[NBR_OF_SAMPLES_MAX];
+    for (float& a : arr) a = f;
+    return new_from_list(arr, lo, hi, n);
+}
+Spectrum new_equal_size_empty_spectrum(const Spectrum& other) {  // :49-58
+    return new_singular_reflectance_factor(other.lo, other.hi, other.nbr_of_samples, 0.0f);
+}
+
+// spectrum.rs:562-594 (f64).
+constexpr double SPEED_OF_LIGHT = 299792458.0;
+constexpr double PLANCK_CONSTANT = 6.62607015e-34;
+constexpr double BOLTZMANN_CONSTANT = 1.380649e-23;
+double black_body_radiation(double wavelength_nm, double temperature_k) {
+    double lambda = wavelength_nm / 1e9;
+    double hc22 = 2.0 * PLANCK_CONSTANT * SPEED_OF_LIGHT * SPEED_OF_LIGHT;
+    double l5 = lambda * lambda * lambda * lambda * lambda;
+    double hc = PLANCK_CONSTANT * SPEED_OF_LIGHT;
+    double ltk = lambda * temperature_k * BOLTZMANN_CONSTANT;
+    double big_denominator = std::exp(hc / ltk) - 1.0;
+    return (hc22 / l5) * (1.0 / big_denominator) * 1e-9;
+}
+
+Spectrum new_temperature_spectrum(float lo, float hi, float temp, size_t n, float mult) {  // :112-122
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    float step = (hi - lo) / (float)(n - 1);
+    for (int i = 0; i < NBR_OF_SAMPLES_MAX; ++i) {
+        float wavelength = lo + step * (float)i;
+        arr[i] = (float)black_body_radiation((double)wavelength, (double)temp) * mult;
+    }
+    return new_from_list(arr, lo, hi, n);
+}
+Spectrum new_sunlight_spectrum(float lo, float hi, size_t n, float mult) {  // :73-96 (6500 K workaround)
+    return new_temperature_spectrum(lo, hi, 6500.0f, n, mult);
+}
+Spectrum new_reflective_spectrum_red(float lo, float hi, size_t n, float f) {  // :141-154
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    float step = (hi - lo) / (float)(n - 1);
+    for (size_t i = 0; i < n; ++i) {
+        float w = lo + step * (float)i;
+        if (550.0f < w) arr[i] = f;
+    }
+    return new_from_list(arr, lo, hi, n);
+}
+Spectrum new_reflective_spectrum_green(float lo, float hi, size_t n, float f) {  // :158-171
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    float step = (hi - lo) / (float)(n - 1);
+    for (size_t i = 0; i < n; ++i) {
+        float w = lo + step * (float)i;
+        if (500.0f < w && w < 575.0f) arr[i] = f;
+    }
+    return new_from_list(arr, lo, hi, n);
+}
+Spectrum new_reflective_spectrum_blue(float lo, float hi, size_t n, float f) {  // :175-187
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    float step = (hi - lo) / (float)(n - 1);
+    for (size_t i = 0; i < n; ++i) {
+        float w = lo + step * (float)i;
+        if (w < 475.0f) arr[i] = f;
+    }
+    return new_from_list(arr, lo, hi, n);
+}
+
+void max0(Spectrum& s) {  // :215-221
+    for (size_t i = 0; i < s.nbr_of_samples; ++i) s.intensities[i] = rmax(s.intensities[i], 0.0f);
+}
+void min1(Spectrum& s) {  // :224-230
+    for (size_t i = 0; i < s.nbr_of_samples; ++i) s.intensities[i] = rmin(s.intensities[i], 1.0f);
+}
+void add_assign(Spectrum& a, const Spectrum& b) {  // :379-388
+    for (size_t i = 0; i < a.nbr_of_samples; ++i) a.intensities[i] += b.intensities[i];
+}
+Spectrum mul(const Spectrum& a, const Spectrum& b) {  // :419-435
+    Spectrum r = a;
+    for (size_t i = 0; i < a.nbr_of_samples; ++i) r.intensities[i] *= b.intensities[i];
+    return r;
+}
+void mul_assign(Spectrum& a, float f) {  // :437-445
+    for (size_t i = 0; i < a.nbr_of_samples; ++i) a.intensities[i] *= f;
+}
+Spectrum div(const Spectrum& a, float f) {  // :447-462
+    Spectrum r = a;
+    for (size_t i = 0; i < a.nbr_of_samples; ++i) r.intensities[i] /= f;
+    return r;
+}
+
+// CIE 1931 2-degree observer, 5 nm, 380..780 nm (data of spectrum.rs:688-770).
+const float CIE_XYZ[81][3] = {
+    {0.00016f, 0.000017f, 0.000705f}, {0.000662f, 0.000072f, 0.002928f}, {0.002362f, 0.000253f, 0.010482f},
+    {0.007242f, 0.000769f, 0.032344f}, {0.01911f, 0.002004f, 0.086011f}, {0.0434f, 0.004509f, 0.197120f},
+    {0.084736f, 0.008756f, 0.389366f}, {0.140638f, 0.014456f, 0.656760f}, {0.204492f, 0.021391f, 0.972542f},
+    {0.264737f, 0.029497f, 1.28250f}, {0.314679f, 0.038676f, 1.55348f}, {0.357719f, 0.049602f, 1.79850f},
+    {0.383734f, 0.062077f, 1.96728f}, {0.386726f, 0.074704f, 2.02730f}, {0.370702f, 0.089456f, 1.99480f},
+    {0.342957f, 0.106256f, 1.90070f}, {0.302273f, 0.128201f, 1.74537f}, {0.254085f, 0.152761f, 1.55490f},
+    {0.195618f, 0.18519f, 1.31756f}, {0.132349f, 0.21994f, 1.03020f}, {0.080507f, 0.253589f, 0.772125f},
+    {0.041072f, 0.297665f, 0.570060f}, {0.016172f, 0.339133f, 0.415254f}, {0.005132f, 0.395379f, 0.302356f},
+    {0.003816f, 0.460777f, 0.218502f}, {0.015444f, 0.53136f, 0.159249f}, {0.037465f, 0.606741f, 0.112044f},
+    {0.071358f, 0.68566f, 0.082248f}, {0.117749f, 0.761757f, 0.060709f}, {0.172953f, 0.82333f, 0.043050f},
+    {0.236491f, 0.875211f, 0.030451f}, {0.304213f, 0.92381f, 0.020584f}, {0.376772f, 0.961988f, 0.013676f},
+    {0.451584f, 0.9822f, 0.007918f}, {0.529826f, 0.991761f, 0.003988f}, {0.616053f, 0.99911f, 0.001091f},
+    {0.705224f, 0.99734f, 0.0f}, {0.793832f, 0.98238f, 0.0f}, {0.878655f, 0.955552f, 0.0f},
+    {0.951162f, 0.915175f, 0.0f}, {1.01416f, 0.868934f, 0.0f}, {1.0743f, 0.825623f, 0.0f},
+    {1.11852f, 0.777405f, 0.0f}, {1.1343f, 0.720353f, 0.0f}, {1.12399f, 0.658341f, 0.0f},
+    {1.0891f, 0.593878f, 0.0f}, {1.03048f, 0.527963f, 0.0f}, {0.95074f, 0.461834f, 0.0f},
+    {0.856297f, 0.398057f, 0.0f}, {0.75493f, 0.339554f, 0.0f}, {0.647467f, 0.283493f, 0.0f},
+    {0.53511f, 0.228254f, 0.0f}, {0.431567f, 0.179828f, 0.0f}, {0.34369f, 0.140211f, 0.0f},
+    {0.268329f, 0.107633f, 0.0f}, {0.2043f, 0.081187f, 0.0f}, {0.152568f, 0.060281f, 0.0f},
+    {0.11221f, 0.044096f, 0.0f}, {0.081261f, 0.0318f, 0.0f}, {0.05793f, 0.022602f, 0.0f},
+    {0.040851f, 0.015905f, 0.0f}, {0.028623f, 0.01113f, 0.0f}, {0.019941f, 0.007749f, 0.0f},
+    {0.013842f, 0.005375f, 0.0f}, {0.009577f, 0.003718f, 0.0f}, {0.006605f, 0.002565f, 0.0f},
+    {0.004553f, 0.001768f, 0.0f}, {0.003145f, 0.001222f, 0.0f}, {0.002175f, 0.000846f, 0.0f},
+    {0.001506f, 0.000586f, 0.0f}, {0.001045f, 0.000407f, 0.0f}, {0.000727f, 0.000284f, 0.0f},
+    {0.000508f, 0.000199f, 0.0f}, {0.000356f, 0.00014f, 0.0f}, {0.000251f, 0.000098f, 0.0f},
+    {0.000178f, 0.00007f, 0.0f}, {0.000126f, 0.00005f, 0.0f}, {0.00009f, 0.000036f, 0.0f},
+    {0.000065f, 0.000025f, 0.0f}, {0.000046f, 0.000018f, 0.0f}, {0.000033f, 0.000013f, 0.0f},
+};
+
+// spectrum.rs:654-681.  NB the interpolation weights are swapped in the
+// reference (lower*fract + upper*(1-fract)); reproduced on purpose.
+V3 wavelength_to_XYZ(float wavelength) {
+    if (!(wavelength >= 380.0f && wavelength <= 780.0f)) return {0.0f, 0.0f, 0.0f};
+    if (std::fmod(wavelength, 5.0f) == 0.0f) {
+        size_t index = ((size_t)wavelength - 380) / 5;
+        return {CIE_XYZ[index][0], CIE_XYZ[index][1], CIE_XYZ[index][2]};
+    }
+    float w_adjusted = (wavelength - 380.0f) / 5.0f;
+    size_t index_lower = (size_t)w_adjusted;
+    size_t index_upper = index_lower + 1;
+    const float* lower = CIE_XYZ[index_lower];
+    const float* upper = CIE_XYZ[index_upper];
+    float fract = w_adjusted - std::trunc(w_adjusted);  // f32::fract
+    float fract_inv = 1.0f - fract;
+    return {lower[0] * fract + upper[0] * fract_inv,
+            lower[1] * fract + upper[1] * fract_inv,
+            lower[2] * fract + upper[2] * fract_inv};
+}
+
+const M3 XYZ_TO_RGB_MATRIX = {{{2.041369f, -0.5649464f, -0.3446944f},   // spectrum.rs:12-16
+                               {-0.969266f, 1.8760108f, 0.0415560f},
+                               {0.0134474f, -0.1183897f, 1.0154096f}}};
+
+// spectrum.rs:238-261.  The wavelength is ACCUMULATED in f32 (`wavelength +=
+// sample_distance` while `wavelength <= max`), so some sample counts generate
+// fewer than nbr_of_samples entries and the trailing intensities are ignored.
+V3 get_rgb_early(const Spectrum& s) {
+    std::vector<V3> xyz_values;
+    xyz_values.reserve(s.nbr_of_samples);
+    float sample_distance = (s.hi - s.lo) / (float)(s.nbr_of_samples - 1);
+    float wavelength = s.lo;
+    while (wavelength <= s.hi) {
+        V3 xyz = wavelength_to_XYZ(wavelength);
+        xyz_values.push_back(xyz / (float)s.nbr_of_samples);
+        wavelength += sample_distance;
+    }
+    for (size_t i = 0; i < xyz_values.size(); ++i) xyz_values[i] = xyz_values[i] * s.intensities[i];
+    V3 fin = {0.0f, 0.0f, 0.0f};
+    for (const V3& v : xyz_values) fin = fin + v;
+    return na::mul(XYZ_TO_RGB_MATRIX, fin);
+}
+
+// ---------------------------------------------------------------- scene types
+struct Material {  // shader.rs:253-258
+    Spectrum reflective_spectrum;
+    float metallicness;
+    float roughness;
+};
+enum class AABBType { PlainBox, Sphere, RotatedBox };  // shader.rs:168-172
+struct Aabb {                                           // shader.rs:99-104
+    V3 min, max;
+    AABBType aabb_type;
+    V3 rb_pos, rb_dim;  // RotatedBox payload
+    M3 rb_rot;
+    Material material;
+    uint32_t material_id;  // bookkeeping only (for exporting the scene to the tests)
+};
+struct Light {  // shader.rs:192-195
+    V3 position;
+    Spectrum spectrum;
+    uint32_t spectrum_id;
+};
+struct Camera {  // shader.rs:213-218
+    V3 position, direction, up;
+    float fov_y_deg;
+};
+struct RaytracingUniforms {  // shader.rs:32-41
+    std::vector<Aabb> aabbs;
+    std::vector<Light> lights;
+    Camera camera;
+    uint32_t frame_id;
+    uint32_t intended_frames_amount;
+    Spectrum example_spectrum;
+    uint32_t max_bounces;
+};
+
+Aabb new_sphere(V3 c, float radius, const Material& m) {  // shader.rs:108-115
+    Aabb a{};
+    a.min = {c.x - radius, c.y - radius, c.z - radius};
+    a.max = {c.x + radius, c.y + radius, c.z + radius};
+    a.aabb_type = AABBType::Sphere;
+    a.material = m;
+    return a;
+}
+Aabb new_box(V3 c, float xl, float yl, float zl, const Material& m) {  // shader.rs:120-130
+    float xh = xl / 2.0f, yh = yl / 2.0f, zh = zl / 2.0f;
+    Aabb a{};
+    a.min = {c.x - xh, c.y - yh, c.z - zh};
+    a.max = {c.x + xh, c.y + yh, c.z + zh};
+    a.aabb_type = AABBType::PlainBox;
+    a.material = m;
+    return a;
+}
+Aabb new_rotated_box(V3 c, float xl, float yl, float zl, const M3& rot, const Material& m) {  // :134-166
+    float xh = xl / 2.0f, yh = yl / 2.0f, zh = zl / 2.0f;
+    const float sx[2] = {-xh, xh}, sy[2] = {-yh, yh}, sz[2] = {-zh, zh};
+    // order of the reference: mmm mmp mpm mpp pmm pmp ppm ppp
+    V3 p[8];
+    int k = 0;
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int l = 0; l < 2; ++l) p[k++] = c + na::mul(rot, V3{sx[i], sy[j], sz[l]});
+    V3 mn = p[0], mx = p[0];
+    for (int i = 1; i < 8; ++i) {
+        mn = {rmin(mn.x, p[i].x), rmin(mn.y, p[i].y), rmin(mn.z, p[i].z)};
+        mx = {rmax(mx.x, p[i].x), rmax(mx.y, p[i].y), rmax(mx.z, p[i].z)};
+    }
+    Aabb a{};
+    a.min = mn;
+    a.max = mx;
+    a.aabb_type = AABBType::RotatedBox;
+    a.rb_pos = c;
+    a.rb_dim = {xl, yl, zl};
+    a.rb_rot = rot;
+    a.material = m;
+    return a;
+}
+
+struct PixelPos { uint32_t x, y; };
+
+struct Ray {  // shader.rs:45-55
+    V3 origin, direction;
+    bool hit;
+    Spectrum spectrum;
+    bool skip_hit_shader;
+    uint32_t max_bounces;
+    PixelPos original_pixel_pos;
+    float hit_distance;
+    float max_hit_distance;
+};
+
+// ---------------------------------------------------------------- counters
+struct Counters {
+    uint64_t rays_primary = 0, rays_continuation = 0, rays_shadow = 0;
+    uint64_t slab_tests = 0, shape_sphere = 0, shape_plain = 0, shape_rotated = 0;
+    uint64_t hits = 0, self_hits = 0, misses = 0, lit = 0, spec_hits = 0, spec_dropped = 0;
+    uint64_t samples = 0;
+    uint64_t depth_hist[129] = {};
+    void add(const Counters& o) {
+        rays_primary += o.rays_primary; rays_continuation += o.rays_continuation; rays_shadow += o.rays_shadow;
+        slab_tests += o.slab_tests; shape_sphere += o.shape_sphere; shape_plain += o.shape_plain;
+        shape_rotated += o.shape_rotated; hits += o.hits; self_hits += o.self_hits; misses += o.misses;
+        lit += o.lit; spec_hits += o.spec_hits; spec_dropped += o.spec_dropped; samples += o.samples;
+        for (int i = 0; i < 129; ++i) depth_hist[i] += o.depth_hist[i];
+    }
+};
+thread_local Counters tl_counters;
+thread_local uint32_t tl_depth = 0;  // hit_shader invocations in the current sample
+
+Ray ray_new(V3 origin, V3 direction, uint32_t max_bounces, PixelPos px, const Spectrum& example) {  // :59-72
+    Ray r;
+    r.origin = origin;
+    r.direction = na::normalize(direction);
+    r.hit = false;
+    r.spectrum = new_equal_size_empty_spectrum(example);
+    r.skip_hit_shader = false;
+    r.max_bounces = max_bounces;
+    r.original_pixel_pos = px;
+    r.hit_distance = 0.0f;
+    r.max_hit_distance = std::numeric_limits<float>::infinity();
+    return r;
+}
+Ray ray_new_shadow(V3 origin, V3 direction, float max_hit_distance, const Spectrum& example) {  // :78-92
+    Ray r;
+    r.origin = origin;
+    r.direction = direction;
+    r.hit = false;
+    r.spectrum = new_equal_size_empty_spectrum(example);
+    r.skip_hit_shader = true;
+    r.max_bounces = 2;
+    r.original_pixel_pos = {0, 0};
+    r.hit_distance = 0.0f;
+    r.max_hit_distance = max_hit_distance;
+    return r;
+}
+
+// ---------------------------------------------------------------- geometry
+// shader.rs:531-556.  Division per axis per call (no hoisting), early exit
+// inside the loop with `t_max <= t_min`.
+std::optional<std::pair<float, float>> ray_aabb_intersection(V3 o, V3 d, V3 pmin, V3 pmax) {
+    tl_counters.slab_tests++;
+    float t_min = -std::numeric_limits<float>::infinity();
+    float t_max = std::numeric_limits<float>::infinity();
+    for (int i = 0; i < 3; ++i) {
+        float inverse_direction = 1.0f / d[i];
+        float t1 = (pmin[i] - o[i]) * inverse_direction;
+        float t2 = (pmax[i] - o[i]) * inverse_direction;
+        float t_near = t1, t_far = t2;
+        if (inverse_direction < 0.0f) { t_near = t2; t_far = t1; }
+        t_min = rmax(t_min, t_near);
+        t_max = rmin(t_max, t_far);
+        if (t_max <= t_min) return std::nullopt;
+    }
+    if (t_max < 0.0f) return std::nullopt;
+    return std::make_pair(t_min, t_max);
+}
+
+struct SphereIntersection { int n; float t1, t2; };  // shader.rs:500-504
+SphereIntersection ray_sphere_intersection(const Ray& ray, V3 sphere_pos, float sphere_rad) {  // :508-527
+    V3 oc = ray.origin - sphere_pos;
+    float a = na::dot(ray.direction, ray.direction);
+    float b = 2.0f * na::dot(oc, ray.direction);
+    float c = na::dot(oc, oc) - sphere_rad * sphere_rad;
+    float discriminant = b * b - 4.0f * a * c;
+    if (discriminant < 0.0f) return {0, 0.0f, 0.0f};
+    if (discriminant == 0.0f) {
+        float t = (-b - std::sqrt(discriminant)) / (2.0f * a);
+        return {1, t, t};
+    }
+    float ds = std::sqrt(discriminant);
+    float t1 = (-b - ds) / (2.0f * a);
+    float t2 = (-b + ds) / (2.0f * a);
+    return {2, t1, t2};
+}
+
+std::optional<std::pair<float, float>> ray_oriented_box_intersection(V3 o, V3 d, V3 position, V3 dimensions,
+                                                                     const M3& rotation) {  // :560-579
+    M3 inv_rotation = na::transpose(rotation);
+    V3 local_o = na::mul(inv_rotation, o - position);
+    V3 local_d = na::mul(inv_rotation, d);
+    V3 half_dims = dimensions * 0.5f;
+    return ray_aabb_intersection(local_o, local_d, -half_dims, half_dims);
+}
+
+V3 plain_box_normal_calculation(const Aabb& aabb, V3 p) {  // :582-605
+    float x = std::fabs(p.x - aabb.min.x) < F32_DELTA ? -1.0f : (std::fabs(p.x - aabb.max.x) < F32_DELTA ? 1.0f : 0.0f);
+    float y = std::fabs(p.y - aabb.min.y) < F32_DELTA ? -1.0f : (std::fabs(p.y - aabb.max.y) < F32_DELTA ? 1.0f : 0.0f);
+    float z = std::fabs(p.z - aabb.min.z) < F32_DELTA ? -1.0f : (std::fabs(p.z - aabb.max.z) < F32_DELTA ? 1.0f : 0.0f);
+    return na::normalize(V3{x, y, z});
+}
+
+V3 rotated_box_normal_calculation(V3 pos, V3 dim, const M3& rotation, V3 p) {  // :608-650
+    M3 inv_rotation = na::transpose(rotation);
+    V3 local_point = na::mul(inv_rotation, p - pos);
+    V3 half_dim = dim * 0.5f;
+    float distance_x = std::fabs(half_dim.x - local_point.x);
+    float distance_y = std::fabs(half_dim.y - local_point.y);
+    float distance_z = std::fabs(half_dim.z - local_point.z);
+    float distance_x_negative = std::fabs(-half_dim.x - local_point.x);
+    float distance_y_negative = std::fabs(-half_dim.y - local_point.y);
+    float distance_z_negative = std::fabs(-half_dim.z - local_point.z);
+    float min_dist = distance_x;
+    V3 normal_local = {1.0f, 0.0f, 0.0f};
+    if (distance_x_negative < min_dist) { min_dist = distance_x_negative; normal_local = {-1.0f, -0.0f, -0.0f}; }
+    if (distance_y < min_dist) { min_dist = distance_y; normal_local = {0.0f, 1.0f, 0.0f}; }
+    if (distance_y_negative < min_dist) { min_dist = distance_y_negative; normal_local = {-0.0f, -1.0f, -0.0f}; }
+    if (distance_z < min_dist) { min_dist = distance_z; normal_local = {0.0f, 0.0f, 1.0f}; }
+    if (distance_z_negative < min_dist) { normal_local = {-0.0f, -0.0f, -1.0f}; }
+    return na::mul(rotation, normal_local);
+}
+
+// ---------------------------------------------------------------- sampling
+float radical_inverse(uint32_t bits) {  // shader.rs:655-662
+    bits = (bits >> 16) | (bits << 16);
+    bits = ((bits & 0x55555555u) << 1) | ((bits & 0xAAAAAAAAu) >> 1);
+    bits = ((bits & 0x33333333u) << 2) | ((bits & 0xCCCCCCCCu) >> 2);
+    bits = ((bits & 0x0F0F0F0Fu) << 4) | ((bits & 0xF0F0F0F0u) >> 4);
+    bits = ((bits & 0x00FF00FFu) << 8) | ((bits & 0xFF00FF00u) >> 8);
+    return (float)bits * 2.3283064e-10f;
+}
+void hammersley(uint32_t n, uint32_t capital_n, float* ox, float* oy) {  // :670-675
+    *ox = ((float)n + 0.5f) / (float)capital_n;
+    *oy = radical_inverse(n + 1);
+}
+void random_pcg3d_raw(uint32_t x, uint32_t y, uint32_t z, uint32_t out[3]) {  // :685-697
+    x = x * 1664525u + 1013904223u;
+    y = y * 1664525u + 1013904223u;
+    z = z * 1664525u + 1013904223u;
+    x = y * z + x;
+    y = z * x + y;
+    z = x * y + z;
+    x ^= x >> 16;
+    y ^= y >> 16;
+    z ^= z >> 16;
+    x = y * z + x;
+    y = z * x + y;
+    z = x * y + z;
+    out[0] = x; out[1] = y; out[2] = z;
+}
+void random_pcg3d(uint32_t x, uint32_t y, uint32_t z, float* rx, float* ry, float* rz) {  // :699-704
+    uint32_t r[3];
+    random_pcg3d_raw(x, y, z, r);
+    float reciprocal = 1.0f / (float)0xffffffffu;
+    *rx = (float)r[0] * reciprocal;
+    *ry = (float)r[1] * reciprocal;
+    *rz = (float)r[2] * reciprocal;
+}
+V3 reflect_vec(V3 incident, V3 normal) {  // :709-711
+    return incident - (2.0f * na::dot(normal, incident)) * normal;
+}
+V3 global_space_random_bounce_direction(float random_x, float random_y, V3 normal) {  // :717-729
+    float theta = std::asin(std::sqrt(random_x));
+    float phi = 2.0f * PI_F * random_y;
+    V3 local_direction = {std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)};
+    V3 up = {0.0f, 1.0f, 0.0f};
+    if (std::fabs(na::dot(normal, up)) > 0.9999f) up = {1.0f, 0.0f, 0.0f};
+    return na::mul(na::face_towards(normal, up), local_direction);
+}
+V3 sample_in_cone(V3 original_direction, float roughness, float random_x, float random_y) {  // :736-755
+    float theta_max = roughness * roughness * FRAC_PI_2_F;
+    float cos_theta = (1.0f - random_x) + random_x * std::cos(theta_max);
+    float sin_theta = std::sqrt(1.0f - cos_theta * cos_theta);
+    float phi = 2.0f * PI_F * random_y;
+    V3 local = {sin_theta * std::cos(phi), sin_theta * std::sin(phi), cos_theta};
+    V3 w = na::normalize(original_direction);
+    V3 a = std::fabs(w.z) < 0.999f ? V3{0.0f, 0.0f, 1.0f} : V3{1.0f, 0.0f, 0.0f};
+    V3 v = na::normalize(na::cross(w, a));
+    V3 u = na::cross(v, w);
+    return na::normalize(u * local.x + v * local.y + w * local.z);
+}
+
+// ---------------------------------------------------------------- shader stages
+void submit_ray(Ray& ray, const RaytracingUniforms& uniforms);
+
+std::optional<float> intersection_shader(const Ray& ray, const Aabb& aabb) {  // shader.rs:302-357
+    switch (aabb.aabb_type) {
+        case AABBType::Sphere: {
+            tl_counters.shape_sphere++;
+            V3 sphere_pos = (aabb.min + aabb.max) * 0.5f;
+            float radius = aabb.max.x - sphere_pos.x;
+            SphereIntersection si = ray_sphere_intersection(ray, sphere_pos, radius);
+            if (si.n == 0) return std::nullopt;
+            if (si.n == 1) return si.t1 >= 0.0f ? std::optional<float>(si.t1) : std::nullopt;
+            float mn = rmin(si.t1, si.t2), mx = rmax(si.t1, si.t2);
+            if (mn >= 0.0f) return mn;
+            if (mx >= 0.0f) return mx;
+            return std::nullopt;
+        }
+        case AABBType::PlainBox: {
+            tl_counters.shape_plain++;
+            auto tt = ray_aabb_intersection(ray.origin, ray.direction, aabb.min, aabb.max);  // unwrap(): always Some
+            tl_counters.slab_tests--;  // the repeated slab test is booked as part of the shape test
+            float t1 = tt->first, t2 = tt->second;
+            float mn = rmin(t1, t2);
+            if (mn >= 0.0f) return mn;
+            return rmax(t1, t2);
+        }
+        case AABBType::RotatedBox: {
+            tl_counters.shape_rotated++;
+            auto tt = ray_oriented_box_intersection(ray.origin, ray.direction, aabb.rb_pos, aabb.rb_dim, aabb.rb_rot);
+            tl_counters.slab_tests--;
+            if (!tt) return std::nullopt;
+            float mn = rmin(tt->first, tt->second), mx = rmax(tt->first, tt->second);
+            if (mn >= 0.0f) return mn;
+            if (mx >= 0.0f) return mx;
+            return std::nullopt;
+        }
+    }
+    return std::nullopt;
+}
+
+void hit_shader(Ray& ray, const Aabb& aabb, float t, const RaytracingUniforms& uniforms) {  // shader.rs:360-455
+    ray.hit = true;
+    ray.hit_distance = t;
+    tl_counters.hits++;
+    if (t < 1e-4f) tl_counters.self_hits++;
+    tl_depth++;
+
+    V3 intersection_point = ray.origin + ray.direction * t;
+    V3 normal;
+    switch (aabb.aabb_type) {
+        case AABBType::PlainBox: normal = plain_box_normal_calculation(aabb, intersection_point); break;
+        case AABBType::Sphere: {
+            V3 sphere_pos = (aabb.min + aabb.max) * 0.5f;
+            normal = na::normalize(intersection_point - sphere_pos);
+            break;
+        }
+        default:
+            normal = rotated_box_normal_calculation(aabb.rb_pos, aabb.rb_dim, aabb.rb_rot, intersection_point);
+    }
+    V3 new_shot_rays_pos = intersection_point + normal * NEW_RAY_POSITION_OFFSET_DISTANCE;
+
+    Spectrum received_spectrum = new_equal_size_empty_spectrum(ray.spectrum);
+    float random_x, random_y, random_z;
+    random_pcg3d(ray.original_pixel_pos.x, ray.original_pixel_pos.y, uniforms.frame_id + ray.max_bounces,
+                 &random_x, &random_y, &random_z);
+
+    if (random_z < aabb.material.metallicness) {
+        tl_counters.spec_hits++;
+        if (ray.max_bounces > 1) {
+            V3 reflected_direction = reflect_vec(ray.direction, normal);
+            V3 direction = aabb.material.roughness < 0.001f
+                               ? reflected_direction
+                               : sample_in_cone(reflected_direction, aabb.material.roughness, random_x, random_y);
+            Ray new_ray = ray_new(new_shot_rays_pos, direction, ray.max_bounces - 1, ray.original_pixel_pos, ray.spectrum);
+            tl_counters.rays_continuation++;
+            submit_ray(new_ray, uniforms);
+            if (new_ray.hit_distance > SPECULAR_MIN_RAY_DISTANCE) add_assign(received_spectrum, new_ray.spectrum);
+            else if (new_ray.hit) tl_counters.spec_dropped++;
+        }
+    } else {
+        for (const Light& light : uniforms.lights) {
+            V3 direction = light.position - new_shot_rays_pos;
+            float distance = na::norm(direction);
+            V3 direction_norm = na::normalize(direction);
+            Ray shadow_ray = ray_new_shadow(new_shot_rays_pos, direction_norm, distance, ray.spectrum);
+            tl_counters.rays_shadow++;
+            submit_ray(shadow_ray, uniforms);
+            if (!shadow_ray.hit) {
+                tl_counters.lit++;
+                Spectrum adjusted = div(light.spectrum, na::norm_squared(direction));
+                mul_assign(adjusted, rmax(na::dot(na::normalize(shadow_ray.direction), normal), 0.0f));
+                mul_assign(adjusted, rmax(na::dot(-ray.direction, normal), 0.0f));
+                add_assign(received_spectrum, adjusted);
+            }
+        }
+        if (ray.max_bounces > 1) {
+            V3 new_direction = global_space_random_bounce_direction(random_x, random_y, normal);
+            Ray new_ray = ray_new(intersection_point, new_direction, ray.max_bounces - 1, ray.original_pixel_pos, ray.spectrum);
+            tl_counters.rays_continuation++;
+            submit_ray(new_ray, uniforms);
+            max0(new_ray.spectrum);
+            add_assign(received_spectrum, new_ray.spectrum);
+        }
+    }
+    ray.spectrum = mul(aabb.material.reflective_spectrum, received_spectrum);
+}
+
+void miss_shader(Ray& ray, const RaytracingUniforms&) {  // shader.rs:460-463
+    ray.spectrum = new_equal_size_empty_spectrum(ray.spectrum);
+    ray.hit = false;
+    tl_counters.misses++;
+}
+
+// shader.rs:468-495: linear scan with slab pre-test, keep t > 0, stable sort,
+// first(); closest beyond max_hit_distance => neither hit nor miss.
+void submit_ray(Ray& ray, const RaytracingUniforms& uniforms) {
+    std::vector<std::pair<const Aabb*, float>> intersections;
+    for (const Aabb& aabb : uniforms.aabbs) {
+        if (ray_aabb_intersection(ray.origin, ray.direction, aabb.min, aabb.max)) {
+            if (auto t = intersection_shader(ray, aabb)) {
+                if (*t > 0.0f) intersections.emplace_back(&aabb, *t);
+            }
+        }
+    }
+    std::stable_sort(intersections.begin(), intersections.end(),
+                     [](const auto& a, const auto& b) { return a.second < b.second; });
+    if (!intersections.empty()) {
+        const Aabb* aabb = intersections.front().first;
+        float t = intersections.front().second;
+        if (t <= ray.max_hit_distance) {
+            if (!ray.skip_hit_shader) hit_shader(ray, *aabb, t, uniforms);
+            else ray.hit = true;
+        }
+    } else {
+        miss_shader(ray, uniforms);
+    }
+}
+
+// shader.rs:271-299 up to (not including) the colour conversion.
+Ray trace_primary(PixelPos pos, uint32_t w, uint32_t h, const RaytracingUniforms& uniforms) {
+    float x = (float)pos.x, y = (float)pos.y;
+    float width = (float)w, height = (float)h;
+    float aspect_ratio = width / height;
+    float fov_half_rad = (uniforms.camera.fov_y_deg / 2.0f) / 180.0f * PI_F;
+    float focal_distance = 1.0f / std::tan(fov_half_rad);
+    float pixel_offset_x, pixel_offset_y;
+    hammersley(uniforms.frame_id, uniforms.intended_frames_amount, &pixel_offset_x, &pixel_offset_y);
+    y = -(((y + pixel_offset_y) / height) * 2.0f - 1.0f);
+    x = (((x + pixel_offset_x) / width) * 2.0f - 1.0f) * aspect_ratio;
+    V3 up = na::normalize(uniforms.camera.up);
+    V3 forward = na::normalize(uniforms.camera.direction);
+    V3 right = na::normalize(na::cross(forward, up));
+    V3 true_up = na::cross(right, forward);
+    V3 dir = forward * focal_distance - right * x + true_up * y;
+    dir = na::normalize(dir);
+    Ray ray = ray_new(uniforms.camera.position, dir, uniforms.max_bounces, pos, uniforms.example_spectrum);
+    tl_counters.rays_primary++;
+    tl_counters.samples++;
+    tl_depth = 0;
+    submit_ray(ray, uniforms);
+    tl_counters.depth_hist[tl_depth > 128 ? 128 : tl_depth]++;
+    return ray;
+}
+
+V3 ray_generation_shader(PixelPos pos, uint32_t w, uint32_t h, const RaytracingUniforms& uniforms) {
+    Ray ray = trace_primary(pos, w, h, uniforms);
+    return get_rgb_early(ray.spectrum);
+}
+
+// ---------------------------------------------------------------- scene container
+struct Scene {
+    uint32_t n_lambda;
+    float lo, hi;
+    std::vector<Spectrum> spectra;
+    std::vector<Material> materials;
+    std::vector<uint32_t> material_spectrum;
+    RaytracingUniforms u;
+};
+
+constexpr float LO = 380.0f, HI = 780.0f;  // spectrum.rs:5-6
+
+uint32_t add_spectrum(Scene& s, const Spectrum& sp) {
+    s.spectra.push_back(sp);
+    return (uint32_t)s.spectra.size() - 1;
+}
+// From<&UIMaterial> + From<&UISpectrum> (spectrum.rs:486-494): reflective spectra are clamped by min1.
+uint32_t add_material(Scene& s, float metallicness, float roughness, uint32_t spectrum_id, bool reflective = true) {
+    Material m;
+    m.reflective_spectrum = s.spectra[spectrum_id];
+    if (reflective) min1(m.reflective_spectrum);
+    m.metallicness = metallicness;
+    m.roughness = roughness;
+    s.materials.push_back(m);
+    s.material_spectrum.push_back(spectrum_id);
+    return (uint32_t)s.materials.size() - 1;
+}
+void push_obj(Scene& s, Aabb a, uint32_t mat) {
+    a.material_id = mat;
+    s.u.aabbs.push_back(a);
+}
+void add_light(Scene& s, V3 p, uint32_t spectrum_id) {
+    Light l;
+    l.position = p;
+    l.spectrum = s.spectra[spectrum_id];
+    l.spectrum_id = spectrum_id;
+    s.u.lights.push_back(l);
+}
+void default_camera(Scene& s) {  // main.rs:1970-1985
+    s.u.camera = {{0.0f, 0.0f, -2.0f}, {0.0f, 0.0f, 1.0f}, {0.0f, 1.0f, 0.0f}, 60.0f};
+}
+
+void preset_cornell(Scene& s) {  // main.rs:1538-1635
+    size_t n = s.n_lambda;
+    uint32_t sun = add_spectrum(s, new_sunlight_spectrum(LO, HI, n, 0.0001f));
+    uint32_t grey = add_spectrum(s, new_singular_reflectance_factor(LO, HI, n, 0.7f));
+    uint32_t red = add_spectrum(s, new_reflective_spectrum_red(LO, HI, n, 1.0f));
+    uint32_t green = add_spectrum(s, new_reflective_spectrum_green(LO, HI, n, 1.0f));
+    add_light(s, {0.0f, 0.9f, 0.0f}, sun);
+    uint32_t m_grey = add_material(s, 0.0f, 0.0f, grey);
+    uint32_t m_green = add_material(s, 0.0f, 0.0f, green);
+    uint32_t m_red = add_material(s, 0.0f, 0.0f, red);
+    push_obj(s, new_box({0.0f, 0.0f, 2.0f}, 2.0f, 2.0f, 2.0f, s.materials[m_grey]), m_grey);
+    push_obj(s, new_box({0.0f, 2.0f, 0.0f}, 2.0f, 2.0f, 2.0f, s.materials[m_grey]), m_grey);
+    push_obj(s, new_box({0.0f, -2.0f, 0.0f}, 2.0f, 2.0f, 2.0f, s.materials[m_grey]), m_grey);
+    push_obj(s, new_box({-2.0f, 0.0f, 0.0f}, 2.0f, 2.0f, 2.0f, s.materials[m_red]), m_red);
+    push_obj(s, new_box({2.0f, 0.0f, 0.0f}, 2.0f, 2.0f, 2.0f, s.materials[m_green]), m_green);
+    push_obj(s, new_rotated_box({0.5f, -0.75f, -0.5f}, 0.5f, 0.5f, 0.5f, na::from_euler_angles(0.0f, 1.0f, 0.0f),
+                                s.materials[m_grey]), m_grey);
+    push_obj(s, new_rotated_box({-0.5f, -0.4f, 0.5f}, 0.5f, 1.2f, 0.5f, na::from_euler_angles(0.0f, -0.5f, 0.0f),
+                                s.materials[m_grey]), m_grey);
+    default_camera(s);
+}
+
+void preset_default(Scene& s) {  // main.rs:1638-1758
+    size_t n = s.n_lambda;
+    uint32_t sun10 = add_spectrum(s, new_sunlight_spectrum(LO, HI, n, 0.001f));
+    uint32_t sun1mil = add_spectrum(s, new_sunlight_spectrum(LO, HI, n, 100.0f));
+    uint32_t grey = add_spectrum(s, new_singular_reflectance_factor(LO, HI, n, 0.7f));
+    uint32_t white = add_spectrum(s, new_singular_reflectance_factor(LO, HI, n, 1.0f));
+    add_light(s, {0.0f, 2.0f, -1.0f}, sun10);
+    add_light(s, {0.0f, 1000.0f, 0.0f}, sun1mil);
+    uint32_t m_mirror = add_material(s, 1.0f, 0.2f, white);
+    uint32_t m_grey = add_material(s, 0.0f, 0.0f, grey);
+    push_obj(s, new_box({-1.5f, 0.0f, 1.0f}, 0.25f, 3.0f, 30.0f, s.materials[m_mirror]), m_mirror);
+    push_obj(s, new_sphere({0.0f, 0.0f, 1.0f}, 1.0f, s.materials[m_grey]), m_grey);
+    push_obj(s, new_sphere({1.0f, 0.0f, 1.0f}, 1.0f, s.materials[m_grey]), m_grey);
+    push_obj(s, new_box({0.0f, -1.0f, 0.0f}, 50.0f, 0.1f, 50.0f, s.materials[m_grey]), m_grey);
+    default_camera(s);
+}
+
+// floor + n_spheres spheres placed with the
+// reference's own hash; the two lights of the default scene.
+void preset_spheres(Scene& s, uint32_t n_spheres) {
+    size_t n = s.n_lambda;
+    uint32_t sun10 = add_spectrum(s, new_sunlight_spectrum(LO, HI, n, 0.001f));
+    uint32_t sun1mil = add_spectrum(s, new_sunlight_spectrum(LO, HI, n, 100.0f));
+    uint32_t grey = add_spectrum(s, new_singular_reflectance_factor(LO, HI, n, 0.7f));
+    uint32_t white = add_spectrum(s, new_singular_reflectance_factor(LO, HI, n, 1.0f));
+    uint32_t red = add_spectrum(s, new_reflective_spectrum_red(LO, HI, n, 1.0f));
+    uint32_t green = add_spectrum(s, new_reflective_spectrum_green(LO, HI, n, 1.0f));
+    uint32_t blue = add_spectrum(s, new_reflective_spectrum_blue(LO, HI, n, 1.0f));
+    add_light(s, {0.0f, 2.0f, -1.0f}, sun10);
+    add_light(s, {0.0f, 1000.0f, 0.0f}, sun1mil);
+    uint32_t mats[8];
+    mats[0] = add_material(s, 0.0f, 0.0f, grey);
+    mats[1] = add_material(s, 0.0f, 0.0f, red);
+    mats[2] = add_material(s, 0.0f, 0.0f, green);
+    mats[3] = add_material(s, 0.0f, 0.0f, blue);
+    mats[4] = add_material(s, 1.0f, 0.0f, white);
+    mats[5] = add_material(s, 1.0f, 0.1f, white);
+    mats[6] = add_material(s, 1.0f, 0.2f, white);
+    mats[7] = add_material(s, 1.0f, 0.4f, white);
+    push_obj(s, new_box({0.0f, -1.0f, 0.0f}, 50.0f, 0.1f, 50.0f, s.materials[mats[0]]), mats[0]);
+    for (uint32_t i = 0; i < n_spheres; ++i) {
+        float u, v, w, p, q, r_;
+        random_pcg3d(i, 0x5EEDu, 1u, &u, &v, &w);
+        random_pcg3d(i, 0x5EEDu, 2u, &p, &q, &r_);
+        float r = 0.03f + 0.09f * w;
+        V3 c = {-8.0f + 16.0f * u, -0.9f + r, 0.0f + 16.0f * v};
+        uint32_t mi = (uint32_t)(8.0f * p);
+        if (mi > 7) mi = 7;
+        push_obj(s, new_sphere(c, r, s.materials[mats[mi]]), mats[mi]);
+    }
+    default_camera(s);
+}
+
+// ---------------------------------------------------------------- frame loop
+// custom_image.rs:59-79
+inline void blend_pixel(float* px, float r, float g, float b, float a, float new_weight_factor) {
+    float old_factor = 1.0f - new_weight_factor;
+    px[0] = px[0] * old_factor + r * new_weight_factor;
+    px[1] = px[1] * old_factor + g * new_weight_factor;
+    px[2] = px[2] * old_factor + b * new_weight_factor;
+    px[3] = px[3] * old_factor + a * new_weight_factor;
+}
+
+std::mutex g_counter_mutex;
+Counters g_counters;
+
+// main.rs:1280-1322: one job per row on a pool of n_threads, rows returned over
+// a channel and blended serially by the calling thread; per-frame barrier.
+// If spectral_sum != nullptr the raw per-sample spectra are also summed per
+// pixel in f64 (test aid only, never part of the timed baseline).
+void apply_shader2(float* img, uint32_t w, uint32_t h, const RaytracingUniforms& uniforms, unsigned n_threads,
+                   double* spectral_sum, uint32_t n_lambda) {
+    std::atomic<uint32_t> next_row{0};
+    std::mutex m;
+    std::condition_variable cv;
+    std::vector<std::pair<uint32_t, std::vector<float>>> done;
+    auto worker = [&]() {
+        tl_counters = Counters();
+        for (;;) {
+            uint32_t y = next_row.fetch_add(1);
+            if (y >= h) break;
+            std::vector<float> row;
+            row.reserve((size_t)w * 4);
+            for (uint32_t x = 0; x < w; ++x) {
+                if (spectral_sum) {
+                    Ray ray = trace_primary({x, y}, w, h, uniforms);
+                    double* dst = spectral_sum + ((size_t)y * w + x) * n_lambda;
+                    for (uint32_t k = 0; k < n_lambda; ++k) dst[k] += (double)ray.spectrum.intensities[k];
+                    V3 rgb = get_rgb_early(ray.spectrum);
+                    row.push_back(rgb.x); row.push_back(rgb.y); row.push_back(rgb.z);
+                } else {
+                    V3 rgb = ray_generation_shader({x, y}, w, h, uniforms);
+                    row.push_back(rgb.x); row.push_back(rgb.y); row.push_back(rgb.z);
+                }
+            }
+            {
+                std::lock_guard<std::mutex> lk(m);
+                done.emplace_back(y, std::move(row));
+            }
+            cv.notify_one();
+        }
+        std::lock_guard<std::mutex> lk(g_counter_mutex);
+        g_counters.add(tl_counters);
+    };
+    std::vector<std::thread> pool;
+    for (unsigned i = 0; i < n_threads; ++i) pool.emplace_back(worker);
+    uint32_t done_rows = 0;
+    float ratio = 1.0f / (float)(uniforms.frame_id + 1);
+    while (done_rows < h) {
+        std::pair<uint32_t, std::vector<float>> item;
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return !done.empty(); });
+            item = std::move(done.back());
+            done.pop_back();
+        }
+        const std::vector<float>& row = item.second;
+        for (uint32_t x = 0; x < w; ++x)
+            blend_pixel(img + ((size_t)item.first * w + x) * 4, row[3 * x], row[3 * x + 1], row[3 * x + 2], 1.0f, ratio);
+        done_rows++;
+    }
+    for (auto& t : pool) t.join();
+}
+
+}  // namespace
+
+// =================================================================== C API
+extern "C" {
+
+struct orc_scene { Scene s; };
+
+orc_scene* orc_scene_new(uint32_t n_lambda) {
+    if (n_lambda % 8 != 0 || n_lambda == 0 || n_lambda > NBR_OF_SAMPLES_MAX) return nullptr;  // spectrum.rs:37-38
+    orc_scene* o = new orc_scene();
+    o->s.n_lambda = n_lambda;
+    o->s.lo = LO;
+    o->s.hi = HI;
+    o->s.u.frame_id = 0;
+    o->s.u.intended_frames_amount = 1;
+    o->s.u.max_bounces = 30;  // main.rs:33
+    o->s.u.example_spectrum = new_singular_reflectance_factor(LO, HI, n_lambda, 0.0f);  // main.rs:1389-1394
+    default_camera(o->s);
+    return o;
+}
+void orc_scene_free(orc_scene* o) { delete o; }
+
+int orc_scene_preset(orc_scene* o, const char* name, uint32_t arg) {
+    std::string n(name);
+    if (n == "cornell") preset_cornell(o->s);
+    else if (n == "default") preset_default(o->s);
+    else if (n == "spheres") preset_spheres(o->s, arg);
+    else return -1;
+    return 0;
+}
+void orc_scene_set_camera(orc_scene* o, const float* pos, const float* dir, const float* up, float fov) {
+    o->s.u.camera = {{pos[0], pos[1], pos[2]}, {dir[0], dir[1], dir[2]}, {up[0], up[1], up[2]}, fov};
+}
+uint32_t orc_scene_add_spectrum(orc_scene* o, const float* v) {
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    std::memcpy(arr, v, sizeof(float) * o->s.n_lambda);
+    return add_spectrum(o->s, new_from_list(arr, LO, HI, o->s.n_lambda));
+}
+uint32_t orc_scene_add_material(orc_scene* o, float metallicness, float roughness, uint32_t spectrum_id) {
+    return add_material(o->s, metallicness, roughness, spectrum_id);
+}
+void orc_scene_add_light(orc_scene* o, const float* p, uint32_t spectrum_id) {
+    add_light(o->s, {p[0], p[1], p[2]}, spectrum_id);
+}
+void orc_scene_add_sphere(orc_scene* o, const float* c, float r, uint32_t mat) {
+    push_obj(o->s, new_sphere({c[0], c[1], c[2]}, r, o->s.materials[mat]), mat);
+}
+void orc_scene_add_box(orc_scene* o, const float* c, const float* len, uint32_t mat) {
+    push_obj(o->s, new_box({c[0], c[1], c[2]}, len[0], len[1], len[2], o->s.materials[mat]), mat);
+}
+void orc_scene_add_rotated_box(orc_scene* o, const float* c, const float* len, const float* euler, uint32_t mat) {
+    push_obj(o->s, new_rotated_box({c[0], c[1], c[2]}, len[0], len[1], len[2],
+                                   na::from_euler_angles(euler[0], euler[1], euler[2]), o->s.materials[mat]), mat);
+}
+
+// ---- export (so the tests can hand the very same scene to the CUDA path)
+uint32_t orc_scene_counts(const orc_scene* o, uint32_t* n_obj, uint32_t* n_mat, uint32_t* n_light, uint32_t* n_spec) {
+    *n_obj = (uint32_t)o->s.u.aabbs.size();
+    *n_mat = (uint32_t)o->s.materials.size();
+    *n_light = (uint32_t)o->s.u.lights.size();
+    *n_spec = (uint32_t)o->s.spectra.size();
+    return o->s.n_lambda;
+}
+// per object 26 floats: min3 max3 kind center3 dims3 rot9(row-major) material
+void orc_scene_export_objects(const orc_scene* o, float* out) {
+    for (const Aabb& a : o->s.u.aabbs) {
+        float* p = out;
+        p[0] = a.min.x; p[1] = a.min.y; p[2] = a.min.z; p[3] = a.max.x; p[4] = a.max.y; p[5] = a.max.z;
+        p[6] = a.aabb_type == AABBType::PlainBox ? 0.0f : (a.aabb_type == AABBType::Sphere ? 1.0f : 2.0f);
+        p[7] = a.rb_pos.x; p[8] = a.rb_pos.y; p[9] = a.rb_pos.z;
+        p[10] = a.rb_dim.x; p[11] = a.rb_dim.y; p[12] = a.rb_dim.z;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) p[13 + 3 * i + j] = a.rb_rot.m[i][j];
+        p[22] = (float)a.material_id;
+        out += 26;
+    }
+}
+// per material: metallicness, roughness, then n_lambda reflectance values (already min1-clamped)
+void orc_scene_export_materials(const orc_scene* o, float* out) {
+    for (const Material& m : o->s.materials) {
+        out[0] = m.metallicness;
+        out[1] = m.roughness;
+        std::memcpy(out + 2, m.reflective_spectrum.intensities, sizeof(float) * o->s.n_lambda);
+        out += 2 + o->s.n_lambda;
+    }
+}
+// per light: position3 then n_lambda emission values
+void orc_scene_export_lights(const orc_scene* o, float* out) {
+    for (const Light& l : o->s.u.lights) {
+        out[0] = l.position.x; out[1] = l.position.y; out[2] = l.position.z;
+        std::memcpy(out + 3, l.spectrum.intensities, sizeof(float) * o->s.n_lambda);
+        out += 3 + o->s.n_lambda;
+    }
+}
+void orc_scene_export_camera(const orc_scene* o, float* out10) {
+    const Camera& c = o->s.u.camera;
+    float v[10] = {c.position.x, c.position.y, c.position.z, c.direction.x, c.direction.y, c.direction.z,
+                   c.up.x, c.up.y, c.up.z, c.fov_y_deg};
+    std::memcpy(out10, v, sizeof(v));
+}
+
+// ---- known-answer entry points
+void orc_hammersley(uint32_t n, uint32_t N, float* out2) { hammersley(n, N, out2, out2 + 1); }
+void orc_pcg3d(uint32_t x, uint32_t y, uint32_t z, uint32_t* raw3, float* f3) {
+    random_pcg3d_raw(x, y, z, raw3);
+    random_pcg3d(x, y, z, f3, f3 + 1, f3 + 2);
+}
+void orc_wavelength_to_xyz(float w, float* out3) {
+    V3 v = wavelength_to_XYZ(w);
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+double orc_black_body(double wavelength_nm, double temperature_k) {
+    if (!(wavelength_nm > 0.0) || !(temperature_k > 0.0)) return std::nan("");  // the reference panics (spectrum.rs:583-584)
+    return black_body_radiation(wavelength_nm, temperature_k);
+}
+void orc_xyz_to_rgb(const float* xyz, float* rgb) {
+    V3 r = na::mul(XYZ_TO_RGB_MATRIX, {xyz[0], xyz[1], xyz[2]});
+    rgb[0] = r.x; rgb[1] = r.y; rgb[2] = r.z;
+}
+void orc_get_rgb_early(const float* intensities, uint32_t n, float lo, float hi, float* rgb) {
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    std::memcpy(arr, intensities, sizeof(float) * n);
+    V3 r = get_rgb_early(new_from_list(arr, lo, hi, n));
+    rgb[0] = r.x; rgb[1] = r.y; rgb[2] = r.z;
+}
+// how many XYZ entries the accumulated-wavelength loop generates (spectrum.rs:244-249)
+uint32_t orc_rgb_loop_count(uint32_t n, float lo, float hi) {
+    float sample_distance = (hi - lo) / (float)(n - 1);
+    float wavelength = lo;
+    uint32_t c = 0;
+    while (wavelength <= hi) { c++; wavelength += sample_distance; }
+    return c;
+}
+// kind: 0 temperature(arg0=T, arg1=mult) 1 flat(arg0) 2 red(arg0) 3 green(arg0) 4 blue(arg0) 5 sunlight(arg0=mult)
+int orc_spectrum_build(uint32_t kind, uint32_t n, float arg0, float arg1, float* out) {
+    Spectrum s;
+    switch (kind) {
+        case 0: s = new_temperature_spectrum(LO, HI, arg0, n, arg1); break;
+        case 1: s = new_singular_reflectance_factor(LO, HI, n, arg0); break;
+        case 2: s = new_reflective_spectrum_red(LO, HI, n, arg0); break;
+        case 3: s = new_reflective_spectrum_green(LO, HI, n, arg0); break;
+        case 4: s = new_reflective_spectrum_blue(LO, HI, n, arg0); break;
+        case 5: s = new_sunlight_spectrum(LO, HI, n, arg0); break;
+        default: return -1;
+    }
+    std::memcpy(out, s.intensities, sizeof(float) * n);
+    return 0;
+}
+void orc_euler_rotation(float roll, float pitch, float yaw, float* out9) {
+    M3 r = na::from_euler_angles(roll, pitch, yaw);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) out9[3 * i + j] = r.m[i][j];
+}
+void orc_cosine_direction(float rx, float ry, const float* n, float* out3) {
+    V3 d = global_space_random_bounce_direction(rx, ry, {n[0], n[1], n[2]});
+    out3[0] = d.x; out3[1] = d.y; out3[2] = d.z;
+}
+void orc_cone_direction(const float* dir, float roughness, float rx, float ry, float* out3) {
+    V3 d = sample_in_cone({dir[0], dir[1], dir[2]}, roughness, rx, ry);
+    out3[0] = d.x; out3[1] = d.y; out3[2] = d.z;
+}
+// custom_image.rs:92-101 (clamp, *255, truncating cast; NaN -> 0)
+void orc_to_rgba8(const float* data, size_t n, uint8_t* out) {
+    for (size_t i = 0; i < n; ++i) {
+        float f = data[i];
+        if (f != f) { out[i] = 0; continue; }
+        f = f < 0.0f ? 0.0f : (f > 1.0f ? 1.0f : f);
+        f *= 255.0f;
+        out[i] = (uint8_t)f;
+    }
+}
+
+// ---- rendering
+// App::render (main.rs:1338-1341) for frame ids [first_frame, first_frame+n_frames):
+// img (w*h*4 f32, CustomImage.data) is blended in place, so a caller can render
+// a contiguous range in several calls.  spectral_sum (optional, w*h*n_lambda f64)
+// receives the per-pixel sum of the raw per-sample spectra.
+int orc_render(orc_scene* o, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t first_frame, uint32_t n_frames,
+               uint32_t intended_frames, uint32_t n_threads, float* img, double* spectral_sum) {
+    if (!o || w == 0 || h == 0) return -1;
+    if (n_threads == 0) n_threads = std::max(1u, std::thread::hardware_concurrency());  // main.rs:2208-2219
+    RaytracingUniforms u = o->s.u;
+    u.max_bounces = max_bounces;
+    u.intended_frames_amount = intended_frames;
+    for (uint32_t f = first_frame; f < first_frame + n_frames; ++f) {
+        u.frame_id = f;
+        RaytracingUniforms per_frame = u;  // main.rs:1340 clones the uniforms every frame
+        apply_shader2(img, w, h, per_frame, n_threads, spectral_sum, o->s.n_lambda);
+    }
+    return 0;
+}
+
+// one sample: raw spectrum (n_lambda floats) + rgb + number of hit_shader calls
+int orc_sample(orc_scene* o, uint32_t w, uint32_t h, uint32_t max_bounces, uint32_t x, uint32_t y, uint32_t frame,
+               uint32_t intended_frames, float* spectrum, float* rgb, uint32_t* depth) {
+    RaytracingUniforms u = o->s.u;
+    u.max_bounces = max_bounces;
+    u.intended_frames_amount = intended_frames;
+    u.frame_id = frame;
+    Ray ray = trace_primary({x, y}, w, h, u);
+    if (spectrum) std::memcpy(spectrum, ray.spectrum.intensities, sizeof(float) * o->s.n_lambda);
+    if (rgb) { V3 c = get_rgb_early(ray.spectrum); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z; }
+    if (depth) *depth = tl_depth;
+    return 0;
+}
+
+// Primary-hit ids for one frame: ids[w*h] (index into the object list, -1 = miss),
+// t[w*h] (hit distance, +inf for a miss) and band[w*h] = 1 where the pixel lies in
+// the stated epsilon band of grazing hits: the two best candidates
+// are within 1e-5*max(1,t) of each other, or any object's slab / shape decision
+// flips when the ray direction is perturbed by 1e-6 (a proxy for "margin within
+// 1e-5 relative").
+int orc_primary(orc_scene* o, uint32_t w, uint32_t h, uint32_t frame, uint32_t intended_frames, int32_t* ids, float* tt,
+                uint8_t* band) {
+    RaytracingUniforms u = o->s.u;
+    u.intended_frames_amount = intended_frames;
+    u.frame_id = frame;
+    const Camera& cam = u.camera;
+    for (uint32_t py = 0; py < h; ++py) {
+        for (uint32_t px = 0; px < w; ++px) {
+            float x = (float)px, y = (float)py, width = (float)w, height = (float)h;
+            float aspect_ratio = width / height;
+            float fov_half_rad = (cam.fov_y_deg / 2.0f) / 180.0f * PI_F;
+            float focal_distance = 1.0f / std::tan(fov_half_rad);
+            float ox, oy;
+            hammersley(u.frame_id, u.intended_frames_amount, &ox, &oy);
+            y = -(((y + oy) / height) * 2.0f - 1.0f);
+            x = (((x + ox) / width) * 2.0f - 1.0f) * aspect_ratio;
+            V3 up = na::normalize(cam.up);
+            V3 forward = na::normalize(cam.direction);
+            V3 right = na::normalize(na::cross(forward, up));
+            V3 true_up = na::cross(right, forward);
+            V3 dir = na::normalize(forward * focal_distance - right * x + true_up * y);
+            Ray ray = ray_new(cam.position, dir, 1, {px, py}, u.example_spectrum);
+            auto scan = [&](const Ray& r, int32_t* best_id, float* best_t, float* second_t) {
+                *best_id = -1;
+                *best_t = std::numeric_limits<float>::infinity();
+                *second_t = std::numeric_limits<float>::infinity();
+                int32_t i = 0;
+                for (const Aabb& a : u.aabbs) {
+                    if (ray_aabb_intersection(r.origin, r.direction, a.min, a.max)) {
+                        if (auto t = intersection_shader(r, a)) {
+                            if (*t > 0.0f) {
+                                if (*t < *best_t) { *second_t = *best_t; *best_t = *t; *best_id = i; }
+                                else if (*t < *second_t) *second_t = *t;
+                            }
+                        }
+                    }
+                    ++i;
+                }
+            };
+            int32_t id; float t, t2;
+            scan(ray, &id, &t, &t2);
+            size_t idx = (size_t)py * w + px;
+            ids[idx] = id;
+            if (tt) tt[idx] = t;
+            if (band) {
+                uint8_t b = 0;
+                if (id >= 0 && std::fabs(t2 - t) <= 1e-5f * std::fmax(1.0f, t)) b = 1;
+                const float eps = 1e-6f;
+                const V3 perturb[4] = {{eps, 0, 0}, {-eps, 0, 0}, {0, eps, 0}, {0, -eps, 0}};
+                for (int k = 0; k < 4 && !b; ++k) {
+                    Ray r2 = ray;
+                    r2.direction = na::normalize(ray.direction + perturb[k]);
+                    int32_t id2; float ta, tb;
+                    scan(r2, &id2, &ta, &tb);
+                    if (id2 != id) b = 1;
+                }
+                band[idx] = b;
+            }
+        }
+    }
+    return 0;
+}
+
+// counters: 14 scalars then 129 depth-histogram bins
+void orc_counters_reset() {
+    std::lock_guard<std::mutex> lk(g_counter_mutex);
+    g_counters = Counters();
+    tl_counters = Counters();
+}
+void orc_counters_get(uint64_t* out) {
+    std::lock_guard<std::mutex> lk(g_counter_mutex);
+    Counters c = g_counters;
+    c.add(tl_counters);  // samples traced on the calling thread (orc_sample / orc_primary)
+    uint64_t v[14] = {c.samples, c.rays_primary, c.rays_continuation, c.rays_shadow, c.slab_tests, c.shape_sphere,
+                      c.shape_plain, c.shape_rotated, c.hits, c.self_hits, c.misses, c.lit, c.spec_hits, c.spec_dropped};
+    std::memcpy(out, v, sizeof(v));
+    std::memcpy(out + 14, c.depth_hist, sizeof(c.depth_hist));
+}
+unsigned orc_hardware_threads() { return std::max(1u, std::thread::hardware_concurrency()); }
+
+}  // extern "C"
