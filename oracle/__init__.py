@@ -77,6 +77,7 @@ def lib():
         L.orc_primary.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), fp,
                                   C.POINTER(C.c_uint8)]
         L.orc_counters_get.argtypes = [C.POINTER(C.c_uint64)]
+        L.orc_set_modes.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32]
         L.orc_hardware_threads.restype = C.c_uint
         _lib = L
     return _lib
@@ -179,6 +180,16 @@ class Scene:
         lib().orc_primary(self._h, w, h, frame, intended_frames, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(t),
                           band.ctypes.data_as(C.POINTER(C.c_uint8)))
         return ids, t, band
+
+
+MATH_NATIVE, MATH_CANONICAL = 0, 1
+RNG_PCG3D, RNG_PHILOX = 0, 1
+
+
+def set_modes(math_mode=MATH_NATIVE, rng_mode=RNG_PCG3D, philox_key=(0, 0)):
+    """Process-wide oracle modes (see oracle.cpp, g_math_mode): math 0 = platform f32 libm
+    (what the reference calls), 1 = correctly rounded; rng 0 = pcg3d (reference), 1 = Philox."""
+    lib().orc_set_modes(math_mode, rng_mode, philox_key[0], philox_key[1])
 
 
 # ---- known-answer helpers

@@ -128,6 +128,26 @@ constexpr float PI_F = 3.14159265358979323846f;               // std::f32::const
 constexpr float FRAC_PI_2_F = 1.57079632679489661923f;
 constexpr int NBR_OF_SAMPLES_MAX = 128;                       // spectrum.rs:8
 
+// ---------------------------------------------------------------- oracle modes
+// math_mode 0 ("native"): sin/cos/asin are the platform's f32 libm, which is what
+// Rust's f32::sin/cos/asin call on Linux (glibc sinf/cosf/asinf) -- the reference's
+// behaviour on this machine, and the setting of the timed CPU baseline.
+// math_mode 1 ("canonical"): correctly rounded f32 results obtained by evaluating
+// in f64 and rounding once.  The reference's results depend on the libm version at
+// this level (glibc 2.39 asinf differs from the correctly rounded value for ~9 % of
+// the inputs the renderer produces); the canonical mode pins them so that the CUDA
+// path's SRT_MATH_EXACT mode can be compared sample by sample.
+// rng_mode 0: random_pcg3d(px, py, frame + remaining_bounces), shader.rs:389-391.
+// rng_mode 1: Philox4x32-10 keyed (pixel, frame, bounce) -- a beyond-reference
+// extension (BASELINE.json north_star), defined here first.
+int g_math_mode = 0;
+int g_rng_mode = 0;
+uint32_t g_philox_key[2] = {0u, 0u};
+
+inline float m_sin(float x) { return g_math_mode ? (float)std::sin((double)x) : std::sin(x); }
+inline float m_cos(float x) { return g_math_mode ? (float)std::cos((double)x) : std::cos(x); }
+inline float m_asin(float x) { return g_math_mode ? (float)std::asin((double)x) : std::asin(x); }
+
 // ---------------------------------------------------------------- Spectrum
 // spectrum.rs:25-30.  Copy type of 528 bytes; every operator result copies all
 // 128 floats no matter what nbr_of_samples is, exactly like the reference.
@@ -337,6 +357,7 @@ struct RaytracingUniforms {  // shader.rs:32-41
     uint32_t intended_frames_amount;
     Spectrum example_spectrum;
     uint32_t max_bounces;
+    uint32_t width = 0;  // bookkeeping for the Philox extension only (pixel index = y*width + x)
 };
 
 Aabb new_sphere(V3 c, float radius, const Material& m) {  // shader.rs:108-115
@@ -550,23 +571,39 @@ void random_pcg3d(uint32_t x, uint32_t y, uint32_t z, float* rx, float* ry, floa
     *ry = (float)r[1] * reciprocal;
     *rz = (float)r[2] * reciprocal;
 }
+// Philox4x32-10 (Salmon et al., SC'11); counter (pixel, frame, bounce, 0).  Extension.
+void random_philox(uint32_t c0, uint32_t c1, uint32_t c2, float* rx, float* ry, float* rz) {
+    uint32_t c3 = 0u, k0 = g_philox_key[0], k1 = g_philox_key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    float reciprocal = 1.0f / (float)0xffffffffu;
+    *rx = (float)c0 * reciprocal;
+    *ry = (float)c1 * reciprocal;
+    *rz = (float)c2 * reciprocal;
+}
 V3 reflect_vec(V3 incident, V3 normal) {  // :709-711
     return incident - (2.0f * na::dot(normal, incident)) * normal;
 }
 V3 global_space_random_bounce_direction(float random_x, float random_y, V3 normal) {  // :717-729
-    float theta = std::asin(std::sqrt(random_x));
+    float theta = m_asin(std::sqrt(random_x));
     float phi = 2.0f * PI_F * random_y;
-    V3 local_direction = {std::sin(theta) * std::cos(phi), std::sin(theta) * std::sin(phi), std::cos(theta)};
+    V3 local_direction = {m_sin(theta) * m_cos(phi), m_sin(theta) * m_sin(phi), m_cos(theta)};
     V3 up = {0.0f, 1.0f, 0.0f};
     if (std::fabs(na::dot(normal, up)) > 0.9999f) up = {1.0f, 0.0f, 0.0f};
     return na::mul(na::face_towards(normal, up), local_direction);
 }
 V3 sample_in_cone(V3 original_direction, float roughness, float random_x, float random_y) {  // :736-755
     float theta_max = roughness * roughness * FRAC_PI_2_F;
-    float cos_theta = (1.0f - random_x) + random_x * std::cos(theta_max);
+    float cos_theta = (1.0f - random_x) + random_x * m_cos(theta_max);
     float sin_theta = std::sqrt(1.0f - cos_theta * cos_theta);
     float phi = 2.0f * PI_F * random_y;
-    V3 local = {sin_theta * std::cos(phi), sin_theta * std::sin(phi), cos_theta};
+    V3 local = {sin_theta * m_cos(phi), sin_theta * m_sin(phi), cos_theta};
     V3 w = na::normalize(original_direction);
     V3 a = std::fabs(w.z) < 0.999f ? V3{0.0f, 0.0f, 1.0f} : V3{1.0f, 0.0f, 0.0f};
     V3 v = na::normalize(na::cross(w, a));
@@ -637,8 +674,12 @@ void hit_shader(Ray& ray, const Aabb& aabb, float t, const RaytracingUniforms& u
 
     Spectrum received_spectrum = new_equal_size_empty_spectrum(ray.spectrum);
     float random_x, random_y, random_z;
-    random_pcg3d(ray.original_pixel_pos.x, ray.original_pixel_pos.y, uniforms.frame_id + ray.max_bounces,
-                 &random_x, &random_y, &random_z);
+    if (g_rng_mode == 0)
+        random_pcg3d(ray.original_pixel_pos.x, ray.original_pixel_pos.y, uniforms.frame_id + ray.max_bounces,
+                     &random_x, &random_y, &random_z);
+    else
+        random_philox(ray.original_pixel_pos.y * uniforms.width + ray.original_pixel_pos.x, uniforms.frame_id,
+                      uniforms.max_bounces - ray.max_bounces, &random_x, &random_y, &random_z);
 
     if (random_z < aabb.material.metallicness) {
         tl_counters.spec_hits++;
@@ -1032,6 +1073,14 @@ void orc_scene_export_camera(const orc_scene* o, float* out10) {
     std::memcpy(out10, v, sizeof(v));
 }
 
+// ---- oracle modes (see the comment at g_math_mode)
+void orc_set_modes(int math_mode, int rng_mode, uint32_t philox_key_lo, uint32_t philox_key_hi) {
+    g_math_mode = math_mode;
+    g_rng_mode = rng_mode;
+    g_philox_key[0] = philox_key_lo;
+    g_philox_key[1] = philox_key_hi;
+}
+
 // ---- known-answer entry points
 void orc_hammersley(uint32_t n, uint32_t N, float* out2) { hammersley(n, N, out2, out2 + 1); }
 void orc_pcg3d(uint32_t x, uint32_t y, uint32_t z, uint32_t* raw3, float* f3) {
@@ -1115,6 +1164,7 @@ int orc_render(orc_scene* o, uint32_t w, uint32_t h, uint32_t max_bounces, uint3
     RaytracingUniforms u = o->s.u;
     u.max_bounces = max_bounces;
     u.intended_frames_amount = intended_frames;
+    u.width = w;
     for (uint32_t f = first_frame; f < first_frame + n_frames; ++f) {
         u.frame_id = f;
         RaytracingUniforms per_frame = u;  // main.rs:1340 clones the uniforms every frame
@@ -1130,6 +1180,7 @@ int orc_sample(orc_scene* o, uint32_t w, uint32_t h, uint32_t max_bounces, uint3
     u.max_bounces = max_bounces;
     u.intended_frames_amount = intended_frames;
     u.frame_id = frame;
+    u.width = w;
     Ray ray = trace_primary({x, y}, w, h, u);
     if (spectrum) std::memcpy(spectrum, ray.spectrum.intensities, sizeof(float) * o->s.n_lambda);
     if (rgb) { V3 c = get_rgb_early(ray.spectrum); rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z; }

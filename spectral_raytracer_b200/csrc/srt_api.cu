@@ -1,0 +1,907 @@
+// srt_api.cu -- the C ABI of include/srt.h on top of the kernels in srt_kernels.cuh.
+//
+// Host-side responsibilities (all citations into /root/reference/src):
+//   * validation that dispatch_render / Spectrum::new do by panicking
+//     (main.rs:1407-1412, spectrum.rs:37-38)
+//   * the pixel-independent part of ray_generation_shader (shader.rs:272-289)
+//   * the xyz(lambda_i)/n weight table of get_rgb_early (spectrum.rs:238-261,
+//     :654-681) -- built once per context instead of once per sample
+//   * the wavefront loop: generate -> extend -> shade, ping-ponging two path pools
+//
+// There is no CPU rendering code in this file and no fallback: without a usable
+// CUDA device every entry point fails with SRT_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/srt.h"
+#include "srt_kernels.cuh"
+
+using namespace srt;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+// CIE 1931 2-degree standard observer, 5 nm steps, 380..780 nm: the data of
+// WAVELENGTH_TO_XYZ_TABLE (spectrum.rs:688-770).
+const float kCie[81][3] = {
+    {0.00016f, 0.000017f, 0.000705f},  {0.000662f, 0.000072f, 0.002928f}, {0.002362f, 0.000253f, 0.010482f},
+    {0.007242f, 0.000769f, 0.032344f}, {0.01911f, 0.002004f, 0.086011f},  {0.0434f, 0.004509f, 0.197120f},
+    {0.084736f, 0.008756f, 0.389366f}, {0.140638f, 0.014456f, 0.656760f}, {0.204492f, 0.021391f, 0.972542f},
+    {0.264737f, 0.029497f, 1.28250f},  {0.314679f, 0.038676f, 1.55348f},  {0.357719f, 0.049602f, 1.79850f},
+    {0.383734f, 0.062077f, 1.96728f},  {0.386726f, 0.074704f, 2.02730f},  {0.370702f, 0.089456f, 1.99480f},
+    {0.342957f, 0.106256f, 1.90070f},  {0.302273f, 0.128201f, 1.74537f},  {0.254085f, 0.152761f, 1.55490f},
+    {0.195618f, 0.18519f, 1.31756f},   {0.132349f, 0.21994f, 1.03020f},   {0.080507f, 0.253589f, 0.772125f},
+    {0.041072f, 0.297665f, 0.570060f}, {0.016172f, 0.339133f, 0.415254f}, {0.005132f, 0.395379f, 0.302356f},
+    {0.003816f, 0.460777f, 0.218502f}, {0.015444f, 0.53136f, 0.159249f},  {0.037465f, 0.606741f, 0.112044f},
+    {0.071358f, 0.68566f, 0.082248f},  {0.117749f, 0.761757f, 0.060709f}, {0.172953f, 0.82333f, 0.043050f},
+    {0.236491f, 0.875211f, 0.030451f}, {0.304213f, 0.92381f, 0.020584f},  {0.376772f, 0.961988f, 0.013676f},
+    {0.451584f, 0.9822f, 0.007918f},   {0.529826f, 0.991761f, 0.003988f}, {0.616053f, 0.99911f, 0.001091f},
+    {0.705224f, 0.99734f, 0.0f},       {0.793832f, 0.98238f, 0.0f},       {0.878655f, 0.955552f, 0.0f},
+    {0.951162f, 0.915175f, 0.0f},      {1.01416f, 0.868934f, 0.0f},       {1.0743f, 0.825623f, 0.0f},
+    {1.11852f, 0.777405f, 0.0f},       {1.1343f, 0.720353f, 0.0f},        {1.12399f, 0.658341f, 0.0f},
+    {1.0891f, 0.593878f, 0.0f},        {1.03048f, 0.527963f, 0.0f},       {0.95074f, 0.461834f, 0.0f},
+    {0.856297f, 0.398057f, 0.0f},      {0.75493f, 0.339554f, 0.0f},       {0.647467f, 0.283493f, 0.0f},
+    {0.53511f, 0.228254f, 0.0f},       {0.431567f, 0.179828f, 0.0f},      {0.34369f, 0.140211f, 0.0f},
+    {0.268329f, 0.107633f, 0.0f},      {0.2043f, 0.081187f, 0.0f},        {0.152568f, 0.060281f, 0.0f},
+    {0.11221f, 0.044096f, 0.0f},       {0.081261f, 0.0318f, 0.0f},        {0.05793f, 0.022602f, 0.0f},
+    {0.040851f, 0.015905f, 0.0f},      {0.028623f, 0.01113f, 0.0f},       {0.019941f, 0.007749f, 0.0f},
+    {0.013842f, 0.005375f, 0.0f},      {0.009577f, 0.003718f, 0.0f},      {0.006605f, 0.002565f, 0.0f},
+    {0.004553f, 0.001768f, 0.0f},      {0.003145f, 0.001222f, 0.0f},      {0.002175f, 0.000846f, 0.0f},
+    {0.001506f, 0.000586f, 0.0f},      {0.001045f, 0.000407f, 0.0f},      {0.000727f, 0.000284f, 0.0f},
+    {0.000508f, 0.000199f, 0.0f},      {0.000356f, 0.00014f, 0.0f},       {0.000251f, 0.000098f, 0.0f},
+    {0.000178f, 0.00007f, 0.0f},       {0.000126f, 0.00005f, 0.0f},       {0.00009f, 0.000036f, 0.0f},
+    {0.000065f, 0.000025f, 0.0f},      {0.000046f, 0.000018f, 0.0f},      {0.000033f, 0.000013f, 0.0f},
+};
+
+// wavelength_to_XYZ, spectrum.rs:654-681 -- including the swapped interpolation
+// weights (lower*fract + upper*(1-fract)).
+void wavelength_to_xyz(float wl, float out[3]) {
+    out[0] = out[1] = out[2] = 0.0f;
+    if (!(wl >= 380.0f && wl <= 780.0f)) return;
+    if (std::fmod(wl, 5.0f) == 0.0f) {
+        size_t idx = ((size_t)wl - 380) / 5;
+        for (int c = 0; c < 3; ++c) out[c] = kCie[idx][c];
+        return;
+    }
+    float w_adj = (wl - 380.0f) / 5.0f;
+    size_t lo = (size_t)w_adj, hi = lo + 1;
+    float fract = w_adj - std::trunc(w_adj);
+    float fract_inv = 1.0f - fract;
+    for (int c = 0; c < 3; ++c) out[c] = kCie[lo][c] * fract + kCie[hi][c] * fract_inv;
+}
+
+// The per-sample weights of get_rgb_early (spectrum.rs:240-249): the wavelength is
+// accumulated in f32 while `wavelength <= max`, each XYZ triple is divided by
+// nbr_of_samples.  Returns how many samples the loop generated (it can be
+// n_lambda - 1); weights = [3][n_lambda], unused tail zero.
+uint32_t build_rgb_weights(uint32_t n_lambda, float lmin, float lmax, std::vector<float>& w) {
+    w.assign((size_t)3 * n_lambda, 0.0f);
+    float sample_distance = (lmax - lmin) / (float)(n_lambda - 1);
+    float wavelength = lmin;
+    uint32_t used = 0;
+    while (wavelength <= lmax && used < n_lambda) {
+        float xyz[3];
+        wavelength_to_xyz(wavelength, xyz);
+        for (int c = 0; c < 3; ++c) w[(size_t)c * n_lambda + used] = xyz[c] / (float)n_lambda;
+        wavelength += sample_distance;
+        ++used;
+    }
+    return used;
+}
+
+struct V3 {
+    float x, y, z;
+};
+V3 sub(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+V3 scale(V3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+float dot3(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+V3 normalize3(V3 a) {
+    float n = std::sqrt(dot3(a, a));
+    return {a.x / n, a.y / n, a.z / n};
+}
+V3 cross3(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+// ------------------------------------------------------------------ BVH (host build)
+struct BuildPrim {
+    float mn[3], mx[3], c[3];
+    uint32_t index;
+};
+
+void build_bvh(const std::vector<DevObject>& objs, std::vector<DevBvhNode>& nodes, std::vector<uint32_t>& prim_index) {
+    const uint32_t n = (uint32_t)objs.size();
+    std::vector<BuildPrim> prims(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        for (int a = 0; a < 3; ++a) {
+            prims[i].mn[a] = objs[i].mn[a];
+            prims[i].mx[a] = objs[i].mx[a];
+            prims[i].c[a] = 0.5f * (objs[i].mn[a] + objs[i].mx[a]);
+        }
+        prims[i].index = i;
+    }
+    nodes.clear();
+    nodes.reserve(2 * n + 1);
+    nodes.push_back(DevBvhNode{});
+    struct Task {
+        uint32_t node, first, count, depth;
+    };
+    std::vector<Task> stack;
+    stack.push_back({0, 0, n, 0});
+    constexpr int kBins = 16;
+    constexpr uint32_t kLeaf = 4;
+    while (!stack.empty()) {
+        Task t = stack.back();
+        stack.pop_back();
+        float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        float cmn[3] = {INFINITY, INFINITY, INFINITY}, cmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (uint32_t i = t.first; i < t.first + t.count; ++i)
+            for (int a = 0; a < 3; ++a) {
+                mn[a] = std::min(mn[a], prims[i].mn[a]);
+                mx[a] = std::max(mx[a], prims[i].mx[a]);
+                cmn[a] = std::min(cmn[a], prims[i].c[a]);
+                cmx[a] = std::max(cmx[a], prims[i].c[a]);
+            }
+        DevBvhNode& nd = nodes[t.node];
+        for (int a = 0; a < 3; ++a) {
+            nd.mn[a] = mn[a];
+            nd.mx[a] = mx[a];
+        }
+        auto make_leaf = [&]() {
+            nodes[t.node].left_or_first = t.first;
+            nodes[t.node].count = t.count;
+        };
+        if (t.count <= kLeaf || t.depth >= 40) {
+            if (t.count <= 64 || t.depth >= 44) {
+                make_leaf();
+                continue;
+            }
+        }
+        // binned SAH over the centroid bounds
+        int best_axis = -1, best_split = -1;
+        float best_cost = INFINITY;
+        auto area = [](const float* a, const float* b) {
+            float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+            return 2.0f * (dx * dy + dy * dz + dz * dx);
+        };
+        for (int a = 0; a < 3; ++a) {
+            float ext = cmx[a] - cmn[a];
+            if (!(ext > 0.0f)) continue;
+            struct Bin {
+                float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+                uint32_t n = 0;
+            } bins[kBins];
+            for (uint32_t i = t.first; i < t.first + t.count; ++i) {
+                int b = std::min(kBins - 1, (int)((prims[i].c[a] - cmn[a]) / ext * kBins));
+                bins[b].n++;
+                for (int k = 0; k < 3; ++k) {
+                    bins[b].mn[k] = std::min(bins[b].mn[k], prims[i].mn[k]);
+                    bins[b].mx[k] = std::max(bins[b].mx[k], prims[i].mx[k]);
+                }
+            }
+            float la[kBins], ra[kBins];
+            uint32_t ln[kBins], rn[kBins];
+            float lmn[3] = {INFINITY, INFINITY, INFINITY}, lmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            uint32_t cnt = 0;
+            for (int b = 0; b < kBins; ++b) {
+                for (int k = 0; k < 3; ++k) {
+                    lmn[k] = std::min(lmn[k], bins[b].mn[k]);
+                    lmx[k] = std::max(lmx[k], bins[b].mx[k]);
+                }
+                cnt += bins[b].n;
+                ln[b] = cnt;
+                la[b] = cnt ? area(lmn, lmx) : 0.0f;
+            }
+            float rmn[3] = {INFINITY, INFINITY, INFINITY}, rmx[3] = {-INFINITY, -INFINITY, -INFINITY};
+            cnt = 0;
+            for (int b = kBins - 1; b >= 0; --b) {
+                for (int k = 0; k < 3; ++k) {
+                    rmn[k] = std::min(rmn[k], bins[b].mn[k]);
+                    rmx[k] = std::max(rmx[k], bins[b].mx[k]);
+                }
+                cnt += bins[b].n;
+                rn[b] = cnt;
+                ra[b] = cnt ? area(rmn, rmx) : 0.0f;
+            }
+            for (int b = 0; b + 1 < kBins; ++b) {
+                if (ln[b] == 0 || rn[b + 1] == 0) continue;
+                float cost = la[b] * (float)ln[b] + ra[b + 1] * (float)rn[b + 1];
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    best_axis = a;
+                    best_split = b;
+                }
+            }
+        }
+        uint32_t mid;
+        if (best_axis < 0) {
+            if (t.count <= 64) {  // all centroids coincide: cannot split spatially
+                make_leaf();
+                continue;
+            }
+            mid = t.first + t.count / 2;
+        } else {
+            float ext = cmx[best_axis] - cmn[best_axis];
+            auto it = std::partition(prims.begin() + t.first, prims.begin() + t.first + t.count, [&](const BuildPrim& p) {
+                int b = std::min(kBins - 1, (int)((p.c[best_axis] - cmn[best_axis]) / ext * kBins));
+                return b <= best_split;
+            });
+            mid = (uint32_t)(it - prims.begin());
+            if (mid == t.first || mid == t.first + t.count) mid = t.first + t.count / 2;
+        }
+        uint32_t left = (uint32_t)nodes.size();
+        nodes.push_back(DevBvhNode{});
+        nodes.push_back(DevBvhNode{});
+        nodes[t.node].left_or_first = left;
+        nodes[t.node].count = 0;
+        stack.push_back({left, t.first, mid - t.first, t.depth + 1});
+        stack.push_back({left + 1, mid, t.first + t.count - mid, t.depth + 1});
+    }
+    prim_index.resize(n);
+    for (uint32_t i = 0; i < n; ++i) prim_index[i] = prims[i].index;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ context
+struct srt_ctx {
+    srt_params params{};
+    SceneParams scene{};
+    int device = 0;
+    bool use_bvh = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    uint32_t capacity = 0;
+    PathPool pool[2]{};
+    float2* hits = nullptr;
+    PoolCtl* ctl = nullptr;
+    PoolCtl* h_ctl = nullptr;  // pinned
+    DevCounters* counters = nullptr;
+    float* accum = nullptr;
+    size_t accum_floats = 0;
+    float* weights = nullptr;
+    uint32_t weights_used = 0;
+    float4* rgba_f32 = nullptr;
+    uchar4* rgba_u8 = nullptr;
+    // scene storage
+    float2* mat_params = nullptr;
+    float4* mat_ext = nullptr;
+    float4* mat_refl = nullptr;
+    DevObject* objects_g = nullptr;
+    DevBvhNode* bvh_nodes = nullptr;
+    uint32_t* bvh_prims = nullptr;
+    uint64_t frames_accumulated = 0;
+    uint64_t iterations = 0, launches = 0;
+    float last_ms = 0.0f;
+    uint64_t last_launches = 0;
+    volatile int abort_flag = 0;
+    // optional per-stage timing (srt_set_profiling)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    uint32_t prof_used = 0;
+    float stage_ms[3] = {0.f, 0.f, 0.f};
+    uint64_t stage_launches[3] = {0, 0, 0};
+    std::string error;
+};
+
+namespace {
+
+int fail(srt_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->error = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, SRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+void free_ctx(srt_ctx* c) {
+    if (!c) return;
+    DeviceGuard g(c->device);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->pool[i].ray_o);
+        cudaFree(c->pool[i].ray_d);
+        cudaFree(c->pool[i].thr);
+    }
+    cudaFree(c->hits);
+    cudaFree(c->ctl);
+    if (c->h_ctl) cudaFreeHost(c->h_ctl);
+    cudaFree(c->counters);
+    cudaFree(c->accum);
+    cudaFree(c->weights);
+    cudaFree(c->rgba_f32);
+    cudaFree(c->rgba_u8);
+    cudaFree(c->mat_params);
+    cudaFree(c->mat_ext);
+    cudaFree(c->mat_refl);
+    cudaFree(c->objects_g);
+    cudaFree(c->bvh_nodes);
+    cudaFree(c->bvh_prims);
+    for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
+    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+    if (c->ev_end) cudaEventDestroy(c->ev_end);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+template <class Accel, bool EXACT, bool PHILOX>
+void launch_shade_nl(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame, dim3 grid) {
+    const PathPool& cur = c->pool[parity];
+    const PathPool& nxt = c->pool[parity ^ 1];
+    float4* acc = reinterpret_cast<float4*>(c->accum);
+    if (c->scene.n_lambda4 == 8)
+        k_shade<Accel, EXACT, PHILOX, 8><<<grid, kBlock, 0, c->stream>>>(c->scene, cur, nxt, c->ctl, parity, c->capacity,
+                                                                        total, first_frame, c->hits, acc, c->counters);
+    else
+        k_shade<Accel, EXACT, PHILOX, 0><<<grid, kBlock, 0, c->stream>>>(c->scene, cur, nxt, c->ctl, parity, c->capacity,
+                                                                        total, first_frame, c->hits, acc, c->counters);
+}
+template <class Accel>
+void launch_shade(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame, dim3 grid) {
+    const bool exact = c->params.math_mode == SRT_MATH_EXACT, philox = c->params.rng_mode == SRT_RNG_PHILOX;
+    if (exact && philox) launch_shade_nl<Accel, true, true>(c, parity, total, first_frame, grid);
+    else if (exact) launch_shade_nl<Accel, true, false>(c, parity, total, first_frame, grid);
+    else if (philox) launch_shade_nl<Accel, false, true>(c, parity, total, first_frame, grid);
+    else launch_shade_nl<Accel, false, false>(c, parity, total, first_frame, grid);
+}
+
+// One wavefront iteration: generate -> extend -> shade.  Grids cover the whole
+// pool; blocks beyond the live range exit at once, so no host round trip is needed
+// to size them.
+cudaEvent_t prof_event(srt_ctx* c) {
+    if (c->prof_used == c->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->prof_events.push_back(e);
+    }
+    cudaEvent_t e = c->prof_events[c->prof_used++];
+    cudaEventRecord(e, c->stream);
+    return e;
+}
+
+// after a stream synchronise: fold the recorded (begin, gen, extend, shade) quadruples
+void prof_collect(srt_ctx* c) {
+    for (uint32_t i = 0; i + 3 < c->prof_used; i += 4)
+        for (int s = 0; s < 3; ++s) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->prof_events[i + s], c->prof_events[i + s + 1]);
+            c->stage_ms[s] += ms;
+            c->stage_launches[s] += 1;
+        }
+    c->prof_used = 0;
+}
+
+void launch_iteration(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame) {
+    dim3 grid((c->capacity + kBlock - 1) / kBlock);
+    if (c->profiling) prof_event(c);
+    k_generate<<<grid, kBlock, 0, c->stream>>>(c->scene, c->pool[parity], c->ctl, parity, c->capacity, total, first_frame,
+                                              c->counters);
+    if (c->profiling) prof_event(c);
+    if (c->use_bvh) {
+        k_extend<AccelBvh><<<grid, kBlock, 0, c->stream>>>(c->scene, c->pool[parity], c->ctl, parity, c->capacity, total,
+                                                          c->hits);
+        if (c->profiling) prof_event(c);
+        launch_shade<AccelBvh>(c, parity, total, first_frame, grid);
+    } else {
+        k_extend<AccelLinear><<<grid, kBlock, 0, c->stream>>>(c->scene, c->pool[parity], c->ctl, parity, c->capacity,
+                                                             total, c->hits);
+        if (c->profiling) prof_event(c);
+        launch_shade<AccelLinear>(c, parity, total, first_frame, grid);
+    }
+    if (c->profiling) prof_event(c);
+    c->launches += 3;
+    c->iterations += 1;
+}
+
+int resolve(srt_ctx* c, bool want_f32, bool want_u8) {
+    DeviceGuard g(c->device);
+    const uint32_t npix = c->scene.npix;
+    if (want_f32 && !c->rgba_f32) CUDA_TRY(c, cudaMalloc(&c->rgba_f32, (size_t)npix * sizeof(float4)));
+    if (want_u8 && !c->rgba_u8) CUDA_TRY(c, cudaMalloc(&c->rgba_u8, (size_t)npix * sizeof(uchar4)));
+    float frames = c->frames_accumulated ? (float)c->frames_accumulated : 1.0f;
+    k_resolve<<<(npix + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->accum, c->weights, npix, c->scene.n_lambda,
+                                                                      c->weights_used, frames,
+                                                                      want_f32 ? c->rgba_f32 : nullptr,
+                                                                      want_u8 ? c->rgba_u8 : nullptr);
+    c->launches += 1;
+    CUDA_TRY(c, cudaGetLastError());
+    return SRT_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ C ABI
+extern "C" {
+
+uint32_t srt_abi_version(void) { return SRT_ABI_VERSION; }
+
+int srt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* srt_last_error(const srt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
+
+int srt_create(const srt_params* params, const srt_camera* camera, const srt_object* objects, uint32_t n_objects,
+               const srt_material* materials, uint32_t n_materials, const srt_light* lights, uint32_t n_lights,
+               const float* spectra, uint32_t n_spectra, srt_ctx** out) {
+    if (!out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!params || !camera) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "params / camera is null");
+    if ((n_objects && !objects) || (n_materials && !materials) || (n_lights && !lights) || (n_spectra && !spectra))
+        return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null scene array with non-zero count");
+    if (params->width == 0 || params->height == 0)
+        return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "image dimensions must be non-zero");
+    if ((uint64_t)params->width * params->height > 0x7fffffffull)
+        return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "image too large");
+    // Spectrum::new asserts, spectrum.rs:37-38
+    if (params->n_lambda == 0 || params->n_lambda % 8 != 0 || params->n_lambda > (uint32_t)kMaxLambda)
+        return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
+    if (params->max_bounces > kRemMask)
+        return fail(nullptr, SRT_ERR_UNSUPPORTED, "max_bounces > 127 (the reference UI allows at most 100)");
+    if (params->intended_frames == 0)
+        return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "intended_frames must be non-zero");
+    if (n_lights > (uint32_t)kMaxLights) return fail(nullptr, SRT_ERR_UNSUPPORTED, "more than 8 lights");
+    for (uint32_t i = 0; i < n_objects; ++i) {
+        if (objects[i].kind > SRT_ROTATED_BOX) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "unknown object kind");
+        if (objects[i].material >= n_materials)
+            return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "object material index out of range");
+    }
+    for (uint32_t i = 0; i < n_materials; ++i)
+        if (materials[i].reflectance >= n_spectra)
+            return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "material spectrum index out of range");
+    for (uint32_t i = 0; i < n_lights; ++i)
+        if (lights[i].spectrum >= n_spectra)
+            return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "light spectrum index out of range");
+    // are_linear_dependent(direction, up), main.rs:1407-1412 / :2200-2203
+    {
+        V3 d{camera->direction[0], camera->direction[1], camera->direction[2]};
+        V3 u{camera->up[0], camera->up[1], camera->up[2]};
+        V3 cr = cross3(d, u);
+        if (std::fabs(cr.x) < kF32Delta && std::fabs(cr.y) < kF32Delta && std::fabs(cr.z) < kF32Delta)
+            return fail(nullptr, SRT_ERR_CAMERA_COLLINEAR, "view direction and up direction are linearly dependent");
+    }
+
+    int n_dev = srt_device_count();
+    if (n_dev <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+    int device = params->device;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return fail(nullptr, SRT_ERR_CUDA, "cudaGetDevice failed");
+    }
+    if (device >= n_dev) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "device ordinal out of range");
+
+    srt_ctx* c = new srt_ctx();
+    c->params = *params;
+    c->device = device;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete c;
+        return fail(nullptr, SRT_ERR_CUDA, "cudaSetDevice failed");
+    }
+    auto bail = [&](int code, const std::string& msg) {
+        free_ctx(c);
+        return fail(nullptr, code, msg);
+    };
+#define CREATE_TRY(expr)                                                                    \
+    do {                                                                                    \
+        cudaError_t e_ = (expr);                                                            \
+        if (e_ != cudaSuccess) return bail(SRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+    SceneParams& sp = c->scene;
+    const uint32_t nl = params->n_lambda, nl4 = nl / 4;
+    sp.width = params->width;
+    sp.height = params->height;
+    sp.npix = params->width * params->height;
+    sp.n_lambda = nl;
+    sp.n_lambda4 = nl4;
+    sp.max_bounces = params->max_bounces;
+    sp.intended_frames = params->intended_frames;
+    sp.n_objects = n_objects;
+    sp.n_lights = n_lights;
+    sp.n_materials = n_materials;
+    sp.philox_key[0] = params->philox_seed_lo;
+    sp.philox_key[1] = params->philox_seed_hi;
+    sp.lambda_min = params->lambda_min;
+    sp.lambda_step = (params->lambda_max - params->lambda_min) / (float)(nl - 1);
+
+    // pixel-independent part of ray_generation_shader, shader.rs:272-289
+    {
+        float width = (float)params->width, height = (float)params->height;
+        sp.cam.aspect = width / height;
+        sp.cam.width_f = width;
+        sp.cam.height_f = height;
+        float fov_half_rad = (camera->fov_y_deg / 2.0f) / 180.0f * 3.14159265358979323846f;
+        float focal_distance = 1.0f / std::tan(fov_half_rad);
+        V3 up = normalize3({camera->up[0], camera->up[1], camera->up[2]});
+        V3 forward = normalize3({camera->direction[0], camera->direction[1], camera->direction[2]});
+        V3 right = normalize3(cross3(forward, up));
+        V3 true_up = cross3(right, forward);
+        V3 ff = scale(forward, focal_distance);
+        sp.cam.pos[0] = camera->position[0]; sp.cam.pos[1] = camera->position[1]; sp.cam.pos[2] = camera->position[2];
+        sp.cam.fwd_focal[0] = ff.x; sp.cam.fwd_focal[1] = ff.y; sp.cam.fwd_focal[2] = ff.z;
+        sp.cam.right[0] = right.x; sp.cam.right[1] = right.y; sp.cam.right[2] = right.z;
+        sp.cam.true_up[0] = true_up.x; sp.cam.true_up[1] = true_up.y; sp.cam.true_up[2] = true_up.z;
+    }
+
+    // primitives
+    std::vector<DevObject> dev_objs(n_objects);
+    for (uint32_t i = 0; i < n_objects; ++i) {
+        const srt_object& o = objects[i];
+        DevObject& d = dev_objs[i];
+        std::memset(&d, 0, sizeof(d));
+        for (int a = 0; a < 3; ++a) {
+            d.mn[a] = o.min[a];
+            d.mx[a] = o.max[a];
+        }
+        d.kind = o.kind;
+        d.material = o.material;
+        if (o.kind == SRT_SPHERE) {
+            // sphere_pos = (min + max) * 0.5, radius = max.x - sphere_pos.x  (shader.rs:305-306)
+            for (int a = 0; a < 3; ++a) d.c[a] = (o.min[a] + o.max[a]) * 0.5f;
+            d.h[0] = o.max[0] - d.c[0];
+        } else if (o.kind == SRT_ROTATED_BOX) {
+            for (int a = 0; a < 3; ++a) {
+                d.c[a] = o.center[a];
+                d.h[a] = o.dims[a] * 0.5f;  // half_dims = *dimensions * 0.5 (shader.rs:568)
+            }
+            for (int a = 0; a < 9; ++a) d.rot[a] = o.rot[a];
+        }
+    }
+    c->use_bvh = n_objects > 0 && (params->accel == SRT_ACCEL_BVH ||
+                                   (params->accel == SRT_ACCEL_AUTO && n_objects > (uint32_t)kMaxConstObjects));
+    if (!c->use_bvh && n_objects > (uint32_t)kMaxConstObjects)
+        return bail(SRT_ERR_UNSUPPORTED, "linear scan supports at most 64 objects; use SRT_ACCEL_AUTO or SRT_ACCEL_BVH");
+    if (c->use_bvh) {
+        std::vector<DevBvhNode> nodes;
+        std::vector<uint32_t> prim_index;
+        build_bvh(dev_objs, nodes, prim_index);
+        CREATE_TRY(cudaMalloc(&c->objects_g, dev_objs.size() * sizeof(DevObject)));
+        CREATE_TRY(cudaMemcpy(c->objects_g, dev_objs.data(), dev_objs.size() * sizeof(DevObject), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&c->bvh_nodes, nodes.size() * sizeof(DevBvhNode)));
+        CREATE_TRY(cudaMemcpy(c->bvh_nodes, nodes.data(), nodes.size() * sizeof(DevBvhNode), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&c->bvh_prims, prim_index.size() * sizeof(uint32_t)));
+        CREATE_TRY(cudaMemcpy(c->bvh_prims, prim_index.data(), prim_index.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        sp.objects_g = c->objects_g;
+        sp.bvh_nodes = c->bvh_nodes;
+        sp.bvh_prims = c->bvh_prims;
+    } else {
+        for (uint32_t i = 0; i < n_objects; ++i) sp.obj[i] = dev_objs[i];
+    }
+
+    // lights
+    for (uint32_t l = 0; l < n_lights; ++l) {
+        for (int a = 0; a < 3; ++a) sp.light_pos[l][a] = lights[l].position[a];
+        std::memcpy(sp.light_e[l], spectra + (size_t)lights[l].spectrum * nl, nl * sizeof(float));
+    }
+    // materials: reflectance transposed to [n_lambda4][n_materials] float4
+    {
+        const uint32_t nm = std::max(1u, n_materials);
+        std::vector<float2> mp(nm, make_float2(0.f, 0.f));
+        std::vector<float4> me(nm, make_float4(0.f, 1.f, 0.f, 0.f));
+        std::vector<float4> mr((size_t)nl4 * nm, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (uint32_t m = 0; m < n_materials; ++m) {
+            mp[m] = make_float2(materials[m].metallicness, materials[m].roughness);
+            me[m] = make_float4(materials[m].transmissive ? 1.0f : 0.0f, materials[m].ior_a, materials[m].ior_b, 0.0f);
+            const float* r = spectra + (size_t)materials[m].reflectance * nl;
+            for (uint32_t k = 0; k < nl4; ++k) mr[(size_t)k * n_materials + m] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        }
+        CREATE_TRY(cudaMalloc(&c->mat_params, nm * sizeof(float2)));
+        CREATE_TRY(cudaMemcpy(c->mat_params, mp.data(), nm * sizeof(float2), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&c->mat_ext, nm * sizeof(float4)));
+        CREATE_TRY(cudaMemcpy(c->mat_ext, me.data(), nm * sizeof(float4), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&c->mat_refl, mr.size() * sizeof(float4)));
+        CREATE_TRY(cudaMemcpy(c->mat_refl, mr.data(), mr.size() * sizeof(float4), cudaMemcpyHostToDevice));
+        sp.mat_params = c->mat_params;
+        sp.mat_ext = c->mat_ext;
+        sp.mat_refl = c->mat_refl;
+    }
+    // colour weights
+    {
+        std::vector<float> w;
+        c->weights_used = build_rgb_weights(nl, params->lambda_min, params->lambda_max, w);
+        CREATE_TRY(cudaMalloc(&c->weights, w.size() * sizeof(float)));
+        CREATE_TRY(cudaMemcpy(c->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+
+    // path pools + accumulation buffer
+    uint32_t cap = params->pool_paths ? params->pool_paths : (1u << 21);
+    cap = std::max(cap, (uint32_t)kBlock);
+    cap = (cap + kBlock - 1) / kBlock * kBlock;
+    c->capacity = cap;
+    CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CREATE_TRY(cudaEventCreate(&c->ev_begin));
+    CREATE_TRY(cudaEventCreate(&c->ev_end));
+    for (int i = 0; i < 2; ++i) {
+        CREATE_TRY(cudaMalloc(&c->pool[i].ray_o, (size_t)cap * sizeof(float4)));
+        CREATE_TRY(cudaMalloc(&c->pool[i].ray_d, (size_t)cap * sizeof(float4)));
+        CREATE_TRY(cudaMalloc(&c->pool[i].thr, (size_t)cap * nl4 * sizeof(float4)));
+    }
+    CREATE_TRY(cudaMalloc(&c->hits, (size_t)cap * sizeof(float2)));
+    CREATE_TRY(cudaMalloc(&c->ctl, 2 * sizeof(PoolCtl)));
+    CREATE_TRY(cudaMallocHost(&c->h_ctl, 2 * sizeof(PoolCtl)));
+    CREATE_TRY(cudaMalloc(&c->counters, sizeof(DevCounters)));
+    CREATE_TRY(cudaMemset(c->counters, 0, sizeof(DevCounters)));
+    c->accum_floats = (size_t)sp.npix * nl;
+    CREATE_TRY(cudaMalloc(&c->accum, c->accum_floats * sizeof(float)));
+    CREATE_TRY(cudaMemset(c->accum, 0, c->accum_floats * sizeof(float)));
+    CREATE_TRY(cudaDeviceSynchronize());
+#undef CREATE_TRY
+    *out = c;
+    return SRT_OK;
+}
+
+void srt_destroy(srt_ctx* ctx) { free_ctx(ctx); }
+
+int srt_abort(srt_ctx* ctx) {
+    if (!ctx) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    ctx->abort_flag = 1;
+    return SRT_OK;
+}
+
+int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    if (n_frames == 0) return SRT_OK;
+    if (n_frames > kMaxFramesPerCall) return fail(c, SRT_ERR_UNSUPPORTED, "too many frames in one call (max 4194304)");
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(c, SRT_ERR_CUDA, "cudaSetDevice failed");
+    const unsigned long long total = (unsigned long long)n_frames * c->scene.npix;
+    const uint64_t launches_before = c->launches;
+
+    for (int s = 0; s < 3; ++s) {
+        c->stage_ms[s] = 0.f;
+        c->stage_launches[s] = 0;
+    }
+    c->prof_used = 0;
+    c->h_ctl[0].count = 0;
+    c->h_ctl[0].pad = 0;
+    c->h_ctl[0].next_sample = 0;
+    c->h_ctl[1] = c->h_ctl[0];
+    CUDA_TRY(c, cudaMemcpyAsync(c->ctl, c->h_ctl, 2 * sizeof(PoolCtl), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev_begin, c->stream));
+
+    // The number of iterations depends on the path lengths, so the host launches
+    // them in chunks and looks at the control block between chunks (one 32-byte
+    // copy); iterations launched after the work ran out exit immediately.
+    int parity = 0;
+    bool done = false, aborted = false;
+    uint32_t chunk = 8;
+    while (!done) {
+        if (c->abort_flag) {
+            aborted = true;
+            break;
+        }
+        for (uint32_t k = 0; k < chunk; ++k) {
+            launch_iteration(c, parity, total, first_frame);
+            parity ^= 1;
+        }
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_ctl, c->ctl, 2 * sizeof(PoolCtl), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (c->profiling) prof_collect(c);
+        const PoolCtl& now = c->h_ctl[parity];
+        done = now.count == 0 && now.next_sample >= total;
+        if (!done) {
+            // remaining work in pool-fills, to size the next chunk (at least the tail of
+            // max_bounces iterations, at most 64 launches between checks)
+            unsigned long long remaining = total - std::min<unsigned long long>(total, now.next_sample);
+            uint32_t est = (uint32_t)std::min<unsigned long long>(64, remaining / c->capacity + 1);
+            chunk = std::max(est, remaining ? 4u : std::min(16u, c->scene.max_bounces + 1));
+        }
+    }
+    CUDA_TRY(c, cudaEventRecord(c->ev_end, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(c->ev_end));
+    CUDA_TRY(c, cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+    c->last_launches = c->launches - launches_before;
+    if (aborted) {
+        c->abort_flag = 0;
+        return fail(c, SRT_ERR_ABORTED, "render aborted");
+    }
+    c->frames_accumulated += n_frames;
+    return SRT_OK;
+}
+
+int srt_clear(srt_ctx* c) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemsetAsync(c->accum, 0, c->accum_floats * sizeof(float), c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->frames_accumulated = 0;
+    return SRT_OK;
+}
+
+uint64_t srt_frames_accumulated(const srt_ctx* c) { return c ? c->frames_accumulated : 0; }
+
+int srt_set_frames_accumulated(srt_ctx* c, uint64_t n) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    c->frames_accumulated = n;
+    return SRT_OK;
+}
+
+void* srt_accum_device_ptr(srt_ctx* c, size_t* n_floats) {
+    if (!c) return nullptr;
+    if (n_floats) *n_floats = c->accum_floats;
+    return c->accum;
+}
+
+void* srt_stream(srt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int srt_read_accum(srt_ctx* c, float* out) {
+    if (!c || !out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->accum, c->accum_floats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SRT_OK;
+}
+
+int srt_write_accum(srt_ctx* c, const float* in, uint64_t n_frames) {
+    if (!c || !in) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemcpyAsync(c->accum, in, c->accum_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->frames_accumulated = n_frames;
+    return SRT_OK;
+}
+
+int srt_resolve_rgba_f32(srt_ctx* c, float* out) {
+    if (!c || !out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = resolve(c, true, false);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->rgba_f32, (size_t)c->scene.npix * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SRT_OK;
+}
+
+int srt_resolve_rgba_u8(srt_ctx* c, uint8_t* out) {
+    if (!c || !out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = resolve(c, false, true);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->rgba_u8, (size_t)c->scene.npix * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SRT_OK;
+}
+
+int srt_resolve_rgba_f32_device(srt_ctx* c, float* d_out) {
+    if (!c || !d_out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    int rc = resolve(c, true, false);
+    if (rc) return rc;
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemcpyAsync(d_out, c->rgba_f32, (size_t)c->scene.npix * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return SRT_OK;
+}
+
+int srt_primary_ids(srt_ctx* c, uint32_t frame, int32_t* ids, float* t) {
+    if (!c || !ids) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(c->device);
+    const uint32_t npix = c->scene.npix;
+    int32_t* d_ids = nullptr;
+    float* d_t = nullptr;
+    CUDA_TRY(c, cudaMalloc(&d_ids, (size_t)npix * sizeof(int32_t)));
+    if (t) {
+        cudaError_t e = cudaMalloc(&d_t, (size_t)npix * sizeof(float));
+        if (e != cudaSuccess) {
+            cudaFree(d_ids);
+            return fail(c, SRT_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    dim3 grid((npix + kBlock - 1) / kBlock);
+    if (c->use_bvh) k_primary<AccelBvh><<<grid, kBlock, 0, c->stream>>>(c->scene, frame, d_ids, d_t);
+    else k_primary<AccelLinear><<<grid, kBlock, 0, c->stream>>>(c->scene, frame, d_ids, d_t);
+    c->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ids, d_ids, (size_t)npix * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t, (size_t)npix * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_ids);
+    cudaFree(d_t);
+    if (e != cudaSuccess) return fail(c, SRT_ERR_CUDA, cudaGetErrorString(e));
+    return SRT_OK;
+}
+
+int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max,
+                        float* rgb) {
+    if (!spectra || !rgb) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    if (n_lambda == 0 || n_lambda % 8 != 0 || n_lambda > (uint32_t)kMaxLambda)
+        return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
+    if (n == 0) return SRT_OK;
+    if (srt_device_count() <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+    std::vector<float> w;
+    uint32_t used = build_rgb_weights(n_lambda, lambda_min, lambda_max, w);
+    float *d_s = nullptr, *d_w = nullptr, *d_rgb = nullptr;
+    cudaError_t e = cudaMalloc(&d_s, (size_t)n * n_lambda * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_w, w.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_rgb, (size_t)n * 3 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_s, spectra, (size_t)n * n_lambda * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_w, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_spectrum_to_rgb<<<(n + kBlock - 1) / kBlock, kBlock>>>(d_s, d_w, n, n_lambda, used, d_rgb);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(rgb, d_rgb, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(d_s);
+    cudaFree(d_w);
+    cudaFree(d_rgb);
+    if (e != cudaSuccess) return fail(nullptr, SRT_ERR_CUDA, cudaGetErrorString(e));
+    return SRT_OK;
+}
+
+int srt_get_counters(srt_ctx* c, srt_counters* out) {
+    if (!c || !out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(c->device);
+    DevCounters h;
+    CUDA_TRY(c, cudaMemcpyAsync(&h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    out->samples = h.v[kCtrSamples];
+    out->rays_primary = h.v[kCtrPrimary];
+    out->rays_continuation = h.v[kCtrContinuation];
+    out->rays_shadow = h.v[kCtrShadow];
+    out->hits = h.v[kCtrHits];
+    out->self_hits = h.v[kCtrSelfHits];
+    out->misses = h.v[kCtrMisses];
+    out->lit = h.v[kCtrLit];
+    out->spec_hits = h.v[kCtrSpecHits];
+    out->spec_dropped = h.v[kCtrSpecDropped];
+    out->iterations = c->iterations;
+    out->kernel_launches = c->launches;
+    return SRT_OK;
+}
+
+int srt_reset_counters(srt_ctx* c) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    DeviceGuard g(c->device);
+    CUDA_TRY(c, cudaMemsetAsync(c->counters, 0, sizeof(DevCounters), c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->iterations = 0;
+    c->launches = 0;
+    return SRT_OK;
+}
+
+int srt_last_render_stats(srt_ctx* c, float* device_ms, uint64_t* kernel_launches) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    if (device_ms) *device_ms = c->last_ms;
+    if (kernel_launches) *kernel_launches = c->last_launches;
+    return SRT_OK;
+}
+
+int srt_set_profiling(srt_ctx* c, int on) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    c->profiling = on != 0;
+    return SRT_OK;
+}
+
+int srt_last_stage_times(srt_ctx* c, float* ms, uint64_t* launches) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    for (int s = 0; s < 3; ++s) {
+        if (ms) ms[s] = c->stage_ms[s];
+        if (launches) launches[s] = c->stage_launches[s];
+    }
+    return SRT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// srt_types.h -- device-side scene layout shared by the host API and the kernels.
+// Everything here is derived from the C-ABI structs of include/srt.h at
+// srt_create time; nothing in this file is visible to callers.
+#pragma once
+#include <cstdint>
+
+namespace srt {
+
+constexpr int kMaxLambda = 128;        // spectrum.rs:8  NBR_OF_SAMPLES_MAX
+constexpr int kMaxConstObjects = 64;   // linear-scan scenes live in the kernel-parameter constant bank
+constexpr int kMaxLights = 8;
+constexpr int kBlock = 256;
+
+constexpr float kF32Delta = 0.00001f;          // shader.rs:7
+constexpr float kNewRayOffset = 0.00001f;      // shader.rs:8
+constexpr float kSpecularMinDistance = 0.0001f;  // shader.rs:14
+
+enum : uint32_t { kPlainBox = 0, kSphere = 1, kRotatedBox = 2 };
+
+// One primitive, 24 words.  For a sphere c = centre and h[0] = radius exactly as
+// intersection_shader re-derives them from the bounds (shader.rs:305-306); for a
+// rotated box c/h/rot are position, dims*0.5 and the row-major Rotation3
+// (shader.rs:560-571); rot_t is not stored, the transpose is applied by indexing.
+struct DevObject {
+    float mn[3];
+    float mx[3];
+    float c[3];
+    float h[3];
+    float rot[9];
+    uint32_t kind;
+    uint32_t material;
+    uint32_t pad[1];
+};
+static_assert(sizeof(DevObject) == 24 * 4, "DevObject is 24 words");
+
+// Host-precomputed camera frame: the part of ray_generation_shader that does not
+// depend on the pixel (shader.rs:272-278, :286-289), evaluated once in f32 with the
+// same operation order, so the device only does IEEE add/mul/div/sqrt per pixel.
+struct DevCamera {
+    float pos[3];
+    float fwd_focal[3];  // forward * focal_distance
+    float right[3];
+    float true_up[3];
+    float aspect;
+    float width_f, height_f;
+};
+
+struct DevBvhNode {  // 32 bytes
+    float mn[3];
+    uint32_t left_or_first;  // inner: index of left child (right = left+1); leaf: first primitive slot
+    float mx[3];
+    uint32_t count;          // 0 = inner node, >0 = leaf with `count` primitives
+};
+
+// Kernel-parameter block (passed __grid_constant__, so it sits in the constant bank
+// and uniform reads are broadcast / folded into instruction operands).
+struct SceneParams {
+    DevCamera cam;
+    uint32_t width, height, npix;
+    uint32_t n_lambda, n_lambda4;
+    uint32_t max_bounces, intended_frames;
+    uint32_t n_objects, n_lights, n_materials;
+    uint32_t philox_key[2];
+    float lambda_min, lambda_step;          // wavelength of sample i = lambda_min + lambda_step * i (dispersion extension)
+    // materials (global memory; tiny, L1-resident)
+    const float2* mat_params;               // [n_materials] (metallicness, roughness)
+    const float4* mat_ext;                  // [n_materials] (transmissive, ior_a, ior_b, 0)
+    const float4* mat_refl;                 // [n_lambda4][n_materials] reflectance, 4 wavelengths per entry
+    // large scenes: primitives + BVH in global memory
+    const DevObject* objects_g;
+    const DevBvhNode* bvh_nodes;
+    const uint32_t* bvh_prims;              // primitive slot -> object index
+    // lights
+    float light_pos[kMaxLights][3];
+    float light_e[kMaxLights][kMaxLambda];  // raw emission spectra
+    // small scenes: primitives in the constant bank
+    DevObject obj[kMaxConstObjects];
+};
+
+// Path-pool state word (ray_d.w): bits 0..6 remaining bounces (Ray::max_bounces,
+// <= 100 in the UI, main.rs:34), bit 7 parent lobe was specular, bit 8 some
+// ancestor was diffuse (its max0 scrubs NaN, shader.rs:448), bit 9 fresh path
+// (throughput == 1), bits 10..31 frame id relative to the render call.
+constexpr uint32_t kRemMask = 0x7Fu;
+constexpr uint32_t kFlagPrevSpec = 1u << 7;
+constexpr uint32_t kFlagDiffAncestor = 1u << 8;
+constexpr uint32_t kFlagFresh = 1u << 9;
+constexpr uint32_t kFlagMono = 0;  // (dispersion extension keeps its hero wavelength in a side array)
+constexpr int kFrameShift = 10;
+constexpr uint32_t kMaxFramesPerCall = 1u << (32 - kFrameShift);
+
+struct PathPool {
+    float4* ray_o;  // origin.xyz, w = pixel index (bits)
+    float4* ray_d;  // direction.xyz, w = state word (bits)
+    float4* thr;    // [n_lambda4][capacity] path throughput
+};
+
+// Double-buffered control block (see srt_kernels.cuh: iteration `it` reads
+// ctl[it&1] and builds ctl[(it+1)&1]).
+struct PoolCtl {
+    uint32_t count;             // live paths handed over by the previous shade
+    uint32_t pad;
+    unsigned long long next_sample;  // next (frame_local * npix + pixel) to generate
+};
+
+struct DevCounters {
+    unsigned long long v[12];
+};
+enum : int {
+    kCtrSamples = 0, kCtrPrimary, kCtrContinuation, kCtrShadow, kCtrHits, kCtrSelfHits,
+    kCtrMisses, kCtrLit, kCtrSpecHits, kCtrSpecDropped
+};
+
+}  // namespace srt

@@ -1,0 +1,117 @@
+"""CPU-only checks of the host logic and the C-ABI library: every symbol include/srt.h declares is
+exported, the C++ host mirror's presets flatten to exactly the oracle's scenes, and the library
+refuses to work (loudly) without a GPU instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import spectral_raytracer_b200 as srt
+from spectral_raytracer_b200 import scenes
+from helpers import flat_from_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "srt.h")).read()
+    declared = set(re.findall(r"\b(srt_[a-z0-9_]+)\s*\(", header))
+    declared -= {"srt_reduce"}  # lives in libsrt_nccl.so (single-process multi-device NCCL)
+    lib = srt.native.lib()
+    assert declared == set(srt.native.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.srt_abi_version() == 1
+    host = scenes.host_lib()
+    for name in scenes.HOST_EXPORTS:
+        assert hasattr(host, name), name
+
+
+def test_abi_struct_sizes_match_header():
+    # no padding: plain 4-byte fields
+    assert C.sizeof(srt.native.SrtObject) == 23 * 4
+    assert C.sizeof(srt.native.SrtMaterial) == 6 * 4
+    assert C.sizeof(srt.native.SrtLight) == 4 * 4
+    assert C.sizeof(srt.native.SrtCamera) == 10 * 4
+    assert C.sizeof(srt.native.SrtParams) == 15 * 4
+    assert C.sizeof(srt.native.SrtCounters) == 12 * 8
+
+
+@pytest.mark.parametrize("name,arg,n_lambda", [("cornell", 0, 32), ("default", 0, 32), ("spheres", 500, 32),
+                                               ("cornell", 0, 64), ("default", 0, 8)])
+def test_host_presets_equal_oracle_scenes(oracle, name, arg, n_lambda):
+    """dispatch_render's uniform assembly in the C++ host mirror vs the oracle's restatement of the same
+    reference code (main.rs:1389-1404, :1538-1758; shader.rs:108-166): bit-identical inputs."""
+    want = flat_from_oracle(oracle.Scene(n_lambda, name, arg))
+    got = scenes.preset(name, n_lambda, arg)
+    assert got.n_lambda == want.n_lambda
+    assert np.array_equal(got.camera, want.camera)
+    assert np.array_equal(got.objects[:, :7].view(np.uint32), want.objects[:, :7].view(np.uint32))
+    rotated = want.objects[:, 6] == 2  # the RotatedBox payload only exists for that kind (shader.rs:171)
+    assert np.array_equal(got.objects[rotated, 7:22].view(np.uint32), want.objects[rotated, 7:22].view(np.uint32))
+    # material / spectrum numbering may differ; compare what each object / light resolves to
+    def obj_material(f, i):
+        m = f.materials[int(f.objects[i, 22])]
+        return m[0], m[1], f.spectra[int(m[2])]
+    for i in range(len(want.objects)):
+        a, b = obj_material(got, i), obj_material(want, i)
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+    assert len(got.lights) == len(want.lights)
+    for a, b in zip(got.lights, want.lights):
+        assert np.array_equal(a[:3], b[:3])
+        assert np.array_equal(got.spectra[int(a[3])], want.spectra[int(b[3])])
+
+
+def test_host_spectrum_constructors_equal_oracle(oracle):
+    L = scenes.host_lib()
+    for n in (8, 32, 128):
+        for kind, a0, a1 in [(0, 6500.0, 1.0), (0, 2000.0, 0.5), (1, 0.7, 0), (2, 1.0, 0), (3, 0.9, 0), (4, 1.0, 0),
+                             (5, 1e-4, 0)]:
+            out = np.zeros(n, np.float32)
+            assert L.srth_spectrum(kind, n, a0, a1, out.ctypes.data_as(C.POINTER(C.c_float))) == 0
+            assert np.array_equal(out, oracle.spectrum(kind, n, a0, a1))
+    # spectrum.rs:832-869
+    assert abs(L.srth_black_body(500.0, 5000.0) - 12107.190590398) / 12107.19 < 1e-4
+    assert np.isnan(L.srth_black_body(500.0, -1.0))  # the reference panics (spectrum.rs:583-584)
+    out = np.zeros(12, np.float32)
+    assert L.srth_spectrum(1, 12, 1.0, 0, out.ctypes.data_as(C.POINTER(C.c_float))) == -1  # spectrum.rs:37
+
+
+def test_prism_preset_is_cornell_plus_glass():
+    f = scenes.preset("prism", 32)
+    c = scenes.preset("cornell", 32)
+    assert len(f.objects) == len(c.objects) + 1
+    glass = f.materials[int(f.objects[-1, 22])]
+    assert glass[3] == 1 and glass[4] == np.float32(1.30) and glass[5] == 6000.0
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    lib = srt.native.lib()
+    if lib.srt_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(srt.SrtError) as e:
+        srt.Renderer(scenes.preset("cornell"), 16, 16)
+    assert e.value.code == srt.native.SRT_ERR_CUDA and "no CPU fallback" in e.value.message
+    with pytest.raises(srt.SrtError):
+        srt.spectrum_to_rgb(np.ones(32, np.float32))
+    with pytest.raises(srt.SrtError):
+        scenes.dispatch_render("cornell", 16, 16, 1)
+
+
+def test_validation_happens_before_the_device_is_touched():
+    """The reference panics on these (main.rs:1407-1412, spectrum.rs:37-38); srt_create returns a status."""
+    import dataclasses
+    flat = scenes.preset("cornell")
+    cam = flat.camera.copy()
+    cam[6:9] = 2.0 * cam[3:6]
+    with pytest.raises(srt.SrtError) as e:
+        srt.Renderer(dataclasses.replace(flat, camera=cam), 8, 8)
+    assert e.value.code == srt.native.SRT_ERR_CAMERA_COLLINEAR
+    with pytest.raises(srt.SrtError) as e:
+        srt.Renderer(dataclasses.replace(flat, n_lambda=20, spectra=flat.spectra[:, :20]), 8, 8)
+    assert e.value.code == srt.native.SRT_ERR_SPECTRUM_SAMPLES
+    with pytest.raises(srt.SrtError) as e:
+        srt.Renderer(flat, 8, 8, max_bounces=200)
+    assert e.value.code == srt.native.SRT_ERR_UNSUPPORTED
