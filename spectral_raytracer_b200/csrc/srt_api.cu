@@ -253,6 +253,8 @@ struct srt_ctx {
     SceneParams scene{};
     int device = 0;
     bool use_bvh = false;
+    bool resident = false;       // SRT_INTEGRATOR_RESIDENT and n_lambda == 32
+    uint32_t resident_grid = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     uint32_t capacity = 0;
@@ -362,6 +364,20 @@ void launch_shade(srt_ctx* c, int parity, unsigned long long total, uint32_t fir
     else if (exact) launch_shade_nl<Accel, true, false>(c, parity, total, first_frame, grid);
     else if (philox) launch_shade_nl<Accel, false, true>(c, parity, total, first_frame, grid);
     else launch_shade_nl<Accel, false, false>(c, parity, total, first_frame, grid);
+}
+
+template <class Accel>
+void launch_resident(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
+    const bool exact = c->params.math_mode == SRT_MATH_EXACT, philox = c->params.rng_mode == SRT_RNG_PHILOX;
+    unsigned long long* next = reinterpret_cast<unsigned long long*>(c->ctl);
+    float4* acc = reinterpret_cast<float4*>(c->accum);
+#define SRT_RES(E, P) \
+    k_resident<Accel, E, P, 8><<<grid, kResidentBlock, 0, c->stream>>>(c->scene, next, total, first_frame, acc, c->counters)
+    if (exact && philox) SRT_RES(true, true);
+    else if (exact) SRT_RES(true, false);
+    else if (philox) SRT_RES(false, true);
+    else SRT_RES(false, false);
+#undef SRT_RES
 }
 
 // One wavefront iteration: generate -> extend -> shade.  Grids cover the whole
@@ -627,6 +643,14 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         CREATE_TRY(cudaMemcpy(c->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
 
+    // integrator: the resident kernel keeps the throughput in registers and is instantiated for the
+    // default spectral width (NBR_OF_SPECTRUM_SAMPLES_DEFAULT = 32, main.rs:32); other widths use the wavefront
+    c->resident = params->integrator == SRT_INTEGRATOR_RESIDENT && nl4 == 8;
+    {
+        cudaDeviceProp prop;
+        CREATE_TRY(cudaGetDeviceProperties(&prop, device));
+        c->resident_grid = (uint32_t)prop.multiProcessorCount * 4u;
+    }
     // path pools + accumulation buffer
     uint32_t cap = params->pool_paths ? params->pool_paths : (1u << 21);
     cap = std::max(cap, (uint32_t)kBlock);
@@ -682,6 +706,25 @@ int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
     c->h_ctl[1] = c->h_ctl[0];
     CUDA_TRY(c, cudaMemcpyAsync(c->ctl, c->h_ctl, 2 * sizeof(PoolCtl), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaEventRecord(c->ev_begin, c->stream));
+
+    if (c->resident) {
+        // one persistent launch: resident_blocks_per_sm CTAs per SM, each warp pulls batches of samples
+        if (c->abort_flag) {
+            c->abort_flag = 0;
+            return fail(c, SRT_ERR_ABORTED, "render aborted");
+        }
+        dim3 grid(c->resident_grid);
+        if (c->use_bvh) launch_resident<AccelBvh>(c, total, first_frame, grid);
+        else launch_resident<AccelLinear>(c, total, first_frame, grid);
+        c->launches += 1;
+        CUDA_TRY(c, cudaGetLastError());
+        CUDA_TRY(c, cudaEventRecord(c->ev_end, c->stream));
+        CUDA_TRY(c, cudaEventSynchronize(c->ev_end));
+        CUDA_TRY(c, cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
+        c->last_launches = c->launches - launches_before;
+        c->frames_accumulated += n_frames;
+        return SRT_OK;
+    }
 
     // The number of iterations depends on the path lengths, so the host launches
     // them in chunks and looks at the control block between chunks (one 32-byte
@@ -857,16 +900,16 @@ int srt_get_counters(srt_ctx* c, srt_counters* out) {
     DevCounters h;
     CUDA_TRY(c, cudaMemcpyAsync(&h, c->counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    out->samples = h.v[kCtrSamples];
-    out->rays_primary = h.v[kCtrPrimary];
-    out->rays_continuation = h.v[kCtrContinuation];
-    out->rays_shadow = h.v[kCtrShadow];
-    out->hits = h.v[kCtrHits];
-    out->self_hits = h.v[kCtrSelfHits];
-    out->misses = h.v[kCtrMisses];
-    out->lit = h.v[kCtrLit];
-    out->spec_hits = h.v[kCtrSpecHits];
-    out->spec_dropped = h.v[kCtrSpecDropped];
+    out->samples = h.v[kCtrSamples * kCtrStride];
+    out->rays_primary = h.v[kCtrPrimary * kCtrStride];
+    out->rays_continuation = h.v[kCtrContinuation * kCtrStride];
+    out->rays_shadow = h.v[kCtrShadow * kCtrStride];
+    out->hits = h.v[kCtrHits * kCtrStride];
+    out->self_hits = h.v[kCtrSelfHits * kCtrStride];
+    out->misses = h.v[kCtrMisses * kCtrStride];
+    out->lit = h.v[kCtrLit * kCtrStride];
+    out->spec_hits = h.v[kCtrSpecHits * kCtrStride];
+    out->spec_dropped = h.v[kCtrSpecDropped * kCtrStride];
     out->iterations = c->iterations;
     out->kernel_launches = c->launches;
     return SRT_OK;

@@ -103,12 +103,13 @@ struct PoolCtl {
     unsigned long long next_sample;  // next (frame_local * npix + pixel) to generate
 };
 
-struct DevCounters {
-    unsigned long long v[12];
-};
 enum : int {
     kCtrSamples = 0, kCtrPrimary, kCtrContinuation, kCtrShadow, kCtrHits, kCtrSelfHits,
-    kCtrMisses, kCtrLit, kCtrSpecHits, kCtrSpecDropped
+    kCtrMisses, kCtrLit, kCtrSpecHits, kCtrSpecDropped, kNumCounters
+};
+constexpr int kCtrStride = 32;  // one counter per 256-byte line
+struct DevCounters {
+    unsigned long long v[kNumCounters * kCtrStride];
 };
 
 }  // namespace srt
