@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the spectral render path (BASELINE.json: samples/s at 1080p
+Cornell box).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...    # the reference's CPU path (oracle)
+
+Workload (config[1] of BASELINE.json): Cornell box (main.rs:1538-1635), 1920x1080, 32 spectral samples,
+30 bounces.  One STEP = one srt_render_frames call of --frames-per-step frames (default 64), i.e. 64 samples
+for every pixel = 132.7 M samples; the default K=16 steps are exactly the 1024 spp of the named config.
+With N GPUs every rank renders its own --frames-per-step frames per step (frame-sharded, weak scaling), and
+the spectral accumulation buffers are summed onto rank 0 with one NCCL reduce inside the timed region.
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom of main()).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WIDTH, HEIGHT, N_LAMBDA, BOUNCES = 1920, 1080, 32, 30
+SCENE = "cornell"
+
+# SURVEY.md 8(d) cost table: f32 lane-operations per event
+COST = dict(slab=28, shape_sphere=46, shape_plain=31, shape_rotated=70, raygen=75, hit_common=36 + 24,
+            normal_plain=15, normal_sphere=18, normal_rotated=51, per_light=45, diffuse_cont=80, specular_cont=72,
+            resolve=15 + 8)
+
+
+def ops_per_sample(c: dict, n_lambda: int, n_lights: int) -> float:
+    """Algorithmic f32 operations per sample from the ORACLE's event counters."""
+    s = c["samples"]
+    shapes = c["shape_sphere"] + c["shape_plain"] + c["shape_rotated"]
+    normal = (COST["normal_sphere"] * c["shape_sphere"] + COST["normal_plain"] * c["shape_plain"] +
+              COST["normal_rotated"] * c["shape_rotated"]) / max(1, shapes)
+    diffuse_hits = c["hits"] - c["spec_hits"]
+    ops = (c["slab_tests"] * COST["slab"] + c["shape_sphere"] * COST["shape_sphere"] +
+           c["shape_plain"] * COST["shape_plain"] + c["shape_rotated"] * COST["shape_rotated"] +
+           s * COST["raygen"] + c["hits"] * (COST["hit_common"] + normal) +
+           c["rays_shadow"] * COST["per_light"] + c["lit"] * 4 * n_lambda +
+           diffuse_hits * (COST["diffuse_cont"] + 2 * n_lambda) + c["spec_hits"] * (COST["specular_cont"] + n_lambda) +
+           c["hits"] * n_lambda + s * (6 * n_lambda + COST["resolve"]))
+    return ops / s
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.idx = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.proc.wait()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(n_frames: int, threads: int, first_frame: int = 0, counters: bool = False):
+    """The reference's CPU path (oracle/oracle.cpp, platform libm, row-per-task pool) on n_frames of the
+    bench workload.  Returns (seconds, samples, counters|None).  The oracle is only ever the baseline here."""
+    import oracle as O
+    O.build()
+    O.set_modes(O.MATH_NATIVE, O.RNG_PCG3D)
+    sc = O.Scene(N_LAMBDA, SCENE)
+    if counters:
+        O.counters_reset()
+    t0 = time.perf_counter()
+    sc.render(WIDTH, HEIGHT, n_frames, first_frame=first_frame, intended_frames=1024, max_bounces=BOUNCES,
+              threads=threads)
+    dt = time.perf_counter() - t0
+    return dt, n_frames * WIDTH * HEIGHT, (O.counters() if counters else None)
+
+
+def run_reference(args, rank: int, world: int):
+    """--impl reference: the reference's own CPU implementation on all host threads; each step is a bounded
+    sample (1 frame of the 1080p Cornell box = 2.07 M samples).  Under torchrun only rank 0 works."""
+    if rank != 0:
+        return
+    import oracle as O
+    threads = O.hardware_threads()
+    for w in range(args.warmup):
+        cpu_reference_run(1, threads, first_frame=w)
+    t = 0.0
+    samples = 0
+    for k in range(args.steps):
+        dt, n, _ = cpu_reference_run(1, threads, first_frame=args.warmup + k)
+        t += dt
+        samples += n
+    value = samples / t
+    line = {
+        "impl": "reference", "metric": "samples/s at 1080p Cornell box", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1, reference=True),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} steps x 1 frame of the 1920x1080 Cornell box (2.07 M samples each), "
+                                   "C++ restatement of the Rust reference (no Rust toolchain in this image)"},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world: int, reference: bool = False) -> dict:
+    return {"workload": f"Cornell box (main.rs:1538-1635) {WIDTH}x{HEIGHT}, {N_LAMBDA} spectral samples, "
+                        f"{BOUNCES} bounces; 1 step = {1 if reference else args.frames_per_step} frame(s) per rank",
+            "scene": SCENE, "width": WIDTH, "height": HEIGHT, "n_lambda": N_LAMBDA, "max_bounces": BOUNCES,
+            "frames_per_step": 1 if reference else args.frames_per_step,
+            "spp_total": (1 if reference else args.frames_per_step) * args.steps * world,
+            "integrator": "cpu" if reference else ("resident" if args.integrator == 1 else "wavefront"),
+            "rng": "pcg3d_reference" if args.rng == 0 else "philox", "math": "fast" if args.math == 0 else "exact",
+            "parallelism": f"frames sharded over {world} GPU(s), NCCL reduce of spectral accumulation buffers",
+            "cache": "working set (265 MB accumulation buffer per GPU) exceeds the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=64)
+    ap.add_argument("--integrator", type=int, default=1, help="0 wavefront, 1 resident")
+    ap.add_argument("--rng", type=int, default=0, help="0 pcg3d (reference), 1 philox")
+    ap.add_argument("--math", type=int, default=0, help="0 fast (CUDA f32 libm), 1 exact")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3  # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import spectral_raytracer_b200 as srt
+    from spectral_raytracer_b200 import scenes
+    from spectral_raytracer_b200.distributed import accum_as_tensor, reduce_sum_
+
+    if not torch.cuda.is_available() or srt.native.lib().srt_device_count() <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the render backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    F, K, W = args.frames_per_step, args.steps, args.warmup
+    npix = WIDTH * HEIGHT
+    total_frames = (K + W) * F * world
+    flat = scenes.preset(SCENE, N_LAMBDA)
+    r = srt.Renderer(flat, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=max(1024, total_frames), rng=args.rng,
+                     math=args.math, integrator=args.integrator, device=local_rank)
+    r.set_profiling(args.integrator == 0)
+    acc_t = accum_as_tensor(r)
+    host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
+    host_np = host_img.numpy()
+
+    def frame_base(step):  # rank-th block of F frames of global step `step`
+        return (step * world + rank) * F
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`)
+    for s in range(W):
+        r.render_frames(frame_base(s), F)
+    if world > 1:  # warm NCCL
+        dist.reduce(acc_t.clone(), dst=0)
+    r.clear()
+    r.reset_counters()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    wall0 = time.perf_counter()
+    render_ms, launches, stage_ms, stage_n = 0.0, 0, [0.0, 0.0, 0.0], [0, 0, 0]
+    for s in range(K):
+        r.render_frames(frame_base(W + s), F)
+        ms, n = r.last_render_stats()
+        render_ms += ms
+        launches += n
+        sm, sn = r.last_stage_times()
+        stage_ms = [a + b for a, b in zip(stage_ms, sm)]
+        stage_n = [a + b for a, b in zip(stage_n, sn)]
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    if world > 1:
+        dist.reduce(acc_t, dst=0)  # spectral accumulation buffers -> rank 0 over NVLink
+        r.frames_accumulated = K * F * world
+    ev1.record()
+    barrier()
+    reduce_ms = ev0.elapsed_time(ev1)
+    wall = time.perf_counter() - wall0
+    clk = clocks.stop()
+    t_rank = torch.tensor([render_ms + reduce_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
+    total_ms = float(t_rank.item())
+    counters = r.counters()
+    csum = torch.tensor([counters[k] for k in ("samples", "rays_primary", "rays_continuation", "rays_shadow", "lit")],
+                        dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(csum)
+    samples, rays = float(csum[0]), float(csum[1] + csum[2] + csum[3])
+    assert samples == K * F * npix * world, (samples, K * F * npix * world)
+    value = samples / (total_ms * 1e-3)
+
+    # ---------------- end to end through the C ABI with host buffers (`e2e`)
+    # per step: render F frames, resolve spectrum -> RGB on the device and read the RGBA f32 image back
+    # into pinned host memory (what App::render does every frame with FrameUpdate, main.rs:1343-1348);
+    # host -> device per step = the kernel-parameter block (scene) of every launch + the control block.
+    r.clear()
+    barrier()
+    e0 = time.perf_counter()
+    e2e_launches = 0
+    for s in range(K):
+        r.render_frames(frame_base(W + s), F)
+        e2e_launches += r.last_render_stats()[1] + 1
+        r.resolve_rgba_f32(host_np)
+    if world > 1:
+        total = reduce_sum_(acc_t, K * F, dst=0)
+        if rank == 0:
+            r.frames_accumulated = total
+            r.resolve_rgba_f32(host_np)
+    barrier()
+    e_rank = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e_rank, op=dist.ReduceOp.MAX)
+    e2e_value = samples / float(e_rank.item())
+    scene_param_bytes = 13 * 1024  # sizeof(SceneParams), passed by value with every launch
+    h2d = int(e2e_launches / K * scene_param_bytes + 32)
+    d2h = int(host_np.nbytes + 32 * max(1, e2e_launches // (3 * K)))
+
+    # ---------------- CPU baseline (rank 0, N=1): bounded sample of the same workload
+    cpu = None
+    oc = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle as O
+        threads = O.hardware_threads()
+        dt, n, oc = cpu_reference_run(1, threads, counters=True)
+        frames = int(min(24, max(1, 12.0 / dt)))
+        dt2, n2, _ = cpu_reference_run(frames, threads, first_frame=1)
+        cpu = {"value": (n + n2) / (dt + dt2), "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": f"{frames + 1} frames of the same 1920x1080 Cornell box ({(n + n2) / 1e6:.1f} M samples, "
+                         f"{dt + dt2:.1f} s), C++ restatement of the Rust reference with its cost structure "
+                         "(row-per-task pool, 528-byte spectra, per-ray Vec + sort, per-sample get_rgb_early)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- rooflines
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    n_launch = max(1, launches if args.integrator == 1 else stage_n[2])
+    kernel_ms = (render_ms if args.integrator == 1 else stage_ms[2]) / n_launch
+    # algorithmic bytes: 576 B of path state per path-bounce (ray 32 B + throughput 4*n_lambda +
+    # radiance 4*n_lambda, read and written) + 4*n_lambda per accumulation write, from THIS run's counters (rank 0)
+    bounces_rank0 = counters["rays_primary"] + counters["rays_continuation"]
+    alg_bytes = bounces_rank0 * 2 * (32 + 4 * N_LAMBDA + 4 * N_LAMBDA) + counters["lit"] * 4 * N_LAMBDA
+    achieved_gbs = alg_bytes / n_launch / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_resident" if args.integrator == 1 else "k_shade",
+                "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                "traffic": None, "peak_source": peak_src,
+                "note": "algorithmic bytes = SURVEY 8(d) HBM-resident path state (576 B per path-bounce + 128 B per lit "
+                        "event); the resident integrator keeps that state in registers, see roofline_fp32 for the "
+                        "bound that applies (north star: FP32 issue rate)"}
+    sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    fp32 = None
+    if oc is not None:
+        ops = ops_per_sample(oc, N_LAMBDA, 1)
+        peak_ops = 148 * 128 * sm_mhz * 1e6
+        fp32 = {"bound": "fp32_issue", "ops_per_sample": ops, "achieved": value * ops / 1e12,
+                "peak": peak_ops / 1e12, "unit": "Tlane-op/s", "frac": value * ops / peak_ops,
+                "note": "SURVEY 8(d) cost table x oracle event counters on the same config; peak = 148 SMs x 128 lanes "
+                        "x SM clock observed during the run"}
+
+    line = {
+        "metric": "samples/s at 1080p Cornell box", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, world),
+        "mrays_per_s": rays / (total_ms * 1e-3) / 1e6,
+        "rays_per_sample": rays / samples,
+        "reduce_ms": reduce_ms, "wall_s_timed_region": wall,
+        "clocks": clk,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "what": "per step: srt_render_frames + srt_resolve_rgba_f32 into pinned host memory"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "roofline_fp32": fp32,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    r.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
