@@ -563,23 +563,34 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         sp.cam.true_up[0] = true_up.x; sp.cam.true_up[1] = true_up.y; sp.cam.true_up[2] = true_up.z;
     }
 
-    // primitives
+    // primitives, sorted by kind (plain boxes, spheres, rotated boxes), original order inside a kind
+    std::vector<uint32_t> order(n_objects);
+    for (uint32_t i = 0; i < n_objects; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        auto rank = [&](uint32_t i) { return objects[i].kind == SRT_PLAIN_BOX ? 0 : (objects[i].kind == SRT_SPHERE ? 1 : 2); };
+        return rank(a) < rank(b);
+    });
     std::vector<DevObject> dev_objs(n_objects);
-    for (uint32_t i = 0; i < n_objects; ++i) {
-        const srt_object& o = objects[i];
-        DevObject& d = dev_objs[i];
+    sp.n_plain = sp.n_sphere = sp.n_rot = 0;
+    for (uint32_t s = 0; s < n_objects; ++s) {
+        const srt_object& o = objects[order[s]];
+        DevObject& d = dev_objs[s];
         std::memset(&d, 0, sizeof(d));
         for (int a = 0; a < 3; ++a) {
             d.mn[a] = o.min[a];
             d.mx[a] = o.max[a];
         }
-        d.kind = o.kind;
+        d.kind_orig = (order[s] << 2) | o.kind;
         d.material = o.material;
-        if (o.kind == SRT_SPHERE) {
+        if (o.kind == SRT_PLAIN_BOX) {
+            sp.n_plain++;
+        } else if (o.kind == SRT_SPHERE) {
+            sp.n_sphere++;
             // sphere_pos = (min + max) * 0.5, radius = max.x - sphere_pos.x  (shader.rs:305-306)
             for (int a = 0; a < 3; ++a) d.c[a] = (o.min[a] + o.max[a]) * 0.5f;
             d.h[0] = o.max[0] - d.c[0];
-        } else if (o.kind == SRT_ROTATED_BOX) {
+        } else {
+            sp.n_rot++;
             for (int a = 0; a < 3; ++a) {
                 d.c[a] = o.center[a];
                 d.h[a] = o.dims[a] * 0.5f;  // half_dims = *dimensions * 0.5 (shader.rs:568)

@@ -17,21 +17,27 @@ constexpr float kSpecularMinDistance = 0.0001f;  // shader.rs:14
 
 enum : uint32_t { kPlainBox = 0, kSphere = 1, kRotatedBox = 2 };
 
-// One primitive, 24 words.  For a sphere c = centre and h[0] = radius exactly as
-// intersection_shader re-derives them from the bounds (shader.rs:305-306); for a
-// rotated box c/h/rot are position, dims*0.5 and the row-major Rotation3
-// (shader.rs:560-571); rot_t is not stored, the transpose is applied by indexing.
-struct DevObject {
+// One primitive = 7 float4 (28 words), read with 128-bit loads.  The scene's primitives are
+// stored sorted by kind (plain boxes, spheres, rotated boxes; original order inside a kind) so
+// the linear scan runs three branch-free loops; `kind_orig` keeps the caller's object index for
+// reporting and for the reference's tie-break (stable sort => lowest original index wins).
+// For a sphere c = centre and h[0] = radius exactly as intersection_shader re-derives them from
+// the bounds (shader.rs:305-306); for a rotated box c/h/rot are position, dims*0.5 and the
+// row-major Rotation3 (shader.rs:560-571); the inverse rotation is applied by transposed indexing.
+struct alignas(16) DevObject {
     float mn[3];
+    uint32_t kind_orig;  // (original index << 2) | kind
     float mx[3];
-    float c[3];
-    float h[3];
-    float rot[9];
-    uint32_t kind;
     uint32_t material;
-    uint32_t pad[1];
+    float c[3];
+    float pad0;
+    float h[3];
+    float pad1;
+    float rot[9];
+    float pad2[3];
 };
-static_assert(sizeof(DevObject) == 24 * 4, "DevObject is 24 words");
+static_assert(sizeof(DevObject) == 28 * 4, "DevObject is 7 float4");
+constexpr int kObjQuads = 7;
 
 // Host-precomputed camera frame: the part of ray_generation_shader that does not
 // depend on the pixel (shader.rs:272-278, :286-289), evaluated once in f32 with the
@@ -60,6 +66,7 @@ struct SceneParams {
     uint32_t n_lambda, n_lambda4;
     uint32_t max_bounces, intended_frames;
     uint32_t n_objects, n_lights, n_materials;
+    uint32_t n_plain, n_sphere, n_rot;      // primitives are sorted by kind in this order
     uint32_t philox_key[2];
     float lambda_min, lambda_step;          // wavelength of sample i = lambda_min + lambda_step * i (dispersion extension)
     // materials (global memory; tiny, L1-resident)
