@@ -660,7 +660,7 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
     {
         cudaDeviceProp prop;
         CREATE_TRY(cudaGetDeviceProperties(&prop, device));
-        c->resident_grid = (uint32_t)prop.multiProcessorCount * 4u;
+        c->resident_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)kResidentBlocksPerSm;
     }
     // path pools + accumulation buffer
     uint32_t cap = params->pool_paths ? params->pool_paths : (1u << 21);
