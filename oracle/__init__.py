@@ -54,6 +54,9 @@ def lib():
         u32p = C.POINTER(C.c_uint32)
         L.orc_scene_counts.argtypes = [C.c_void_p, u32p, u32p, u32p, u32p]
         L.orc_scene_counts.restype = C.c_uint32
+        L.orc_scene_add_glass.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float]
+        L.orc_scene_add_glass.restype = C.c_uint32
+        L.orc_scene_export_materials_ext.argtypes = [C.c_void_p, fp]
         for n in ("objects", "materials", "lights", "camera"):
             getattr(L, "orc_scene_export_" + n).argtypes = [C.c_void_p, fp]
         L.orc_hammersley.argtypes = [C.c_uint32, C.c_uint32, fp]
@@ -121,6 +124,10 @@ class Scene:
     def add_material(self, metallicness, roughness, spectrum_id) -> int:
         return lib().orc_scene_add_material(self._h, metallicness, roughness, spectrum_id)
 
+    def add_glass(self, spectrum_id, ior_a, ior_b) -> int:
+        """extension: dispersive dielectric, n(lambda) = ior_a + ior_b / lambda_nm^2"""
+        return lib().orc_scene_add_glass(self._h, spectrum_id, ior_a, ior_b)
+
     def add_light(self, pos, spectrum_id):
         lib().orc_scene_add_light(self._h, _f3(pos), spectrum_id)
 
@@ -149,7 +156,10 @@ class Scene:
         if n_light:
             lib().orc_scene_export_lights(self._h, _fp(lig))
         lib().orc_scene_export_camera(self._h, _fp(cam))
-        return {"n_lambda": nl, "objects": obj, "materials": mat, "lights": lig, "camera": cam}
+        ext = np.zeros((n_mat, 3), np.float32)
+        if n_mat:
+            lib().orc_scene_export_materials_ext(self._h, _fp(ext))
+        return {"n_lambda": nl, "objects": obj, "materials": mat, "lights": lig, "camera": cam, "materials_ext": ext}
 
     # ---- rendering
     def render(self, w, h, n_frames, *, first_frame=0, intended_frames=None, max_bounces=30, threads=0,

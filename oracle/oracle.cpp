@@ -330,6 +330,9 @@ struct Material {  // shader.rs:253-258
     Spectrum reflective_spectrum;
     float metallicness;
     float roughness;
+    // beyond-reference dispersion extension (BASELINE.json config 3), see glass_interaction()
+    bool transmissive = false;
+    float ior_a = 1.0f, ior_b = 0.0f;  // Cauchy: n(lambda) = ior_a + ior_b / lambda_nm^2
 };
 enum class AABBType { PlainBox, Sphere, RotatedBox };  // shader.rs:168-172
 struct Aabb {                                           // shader.rs:99-104
@@ -413,6 +416,7 @@ struct Ray {  // shader.rs:45-55
     PixelPos original_pixel_pos;
     float hit_distance;
     float max_hit_distance;
+    int hero = -1;  // extension: index of the single wavelength this path carries after a dispersive hit
 };
 
 // ---------------------------------------------------------------- counters
@@ -681,7 +685,56 @@ void hit_shader(Ray& ray, const Aabb& aabb, float t, const RaytracingUniforms& u
         random_philox(ray.original_pixel_pos.y * uniforms.width + ray.original_pixel_pos.x, uniforms.frame_id,
                       uniforms.max_bounces - ray.max_bounces, &random_x, &random_y, &random_z);
 
-    if (random_z < aabb.material.metallicness) {
+    if (aabb.material.transmissive) {
+        // ---- EXTENSION (no counterpart in the reference, which has no refraction at all): smooth
+        // dielectric with a wavelength-dependent index.  The first dispersive hit of a path collapses it to
+        // one "hero" wavelength h = floor(random_x * n) (radiance of that wavelength is weighted by n, all
+        // others by 0); Snell + unpolarised Fresnel, reflect with probability F (random_z), else refract.
+        // No direct light (delta BSDF); the material's reflective spectrum tints the path like a metal's.
+        const size_t n = ray.spectrum.nbr_of_samples;
+        int hero = ray.hero;
+        float weight = 1.0f;
+        if (hero < 0) {
+            size_t h = (size_t)(random_x * (float)n);
+            hero = (int)(h < n ? h : n - 1);
+            weight = (float)n;
+        }
+        if (ray.max_bounces > 1) {
+            const float step = (ray.spectrum.hi - ray.spectrum.lo) / (float)(n - 1);
+            const float lambda = ray.spectrum.lo + step * (float)hero;
+            const float ior = aabb.material.ior_a + aabb.material.ior_b / (lambda * lambda);
+            const float cosi = na::dot(-ray.direction, normal);
+            const bool entering = cosi > 0.0f;
+            const V3 nf = entering ? normal : -normal;
+            const float ci = entering ? cosi : -cosi;
+            const float n1 = entering ? 1.0f : ior, n2 = entering ? ior : 1.0f;
+            const float eta = n1 / n2;
+            const float sin2t = (eta * eta) * (1.0f - ci * ci);
+            bool reflect = true;
+            float ct = 0.0f;
+            if (!(sin2t > 1.0f)) {  // otherwise total internal reflection
+                ct = std::sqrt(1.0f - sin2t);
+                const float rs = (n1 * ci - n2 * ct) / (n1 * ci + n2 * ct);
+                const float rp = (n2 * ci - n1 * ct) / (n2 * ci + n1 * ct);
+                const float fresnel = (rs * rs + rp * rp) * 0.5f;
+                reflect = random_z < fresnel;
+            }
+            V3 direction, origin;
+            if (reflect) {
+                direction = reflect_vec(ray.direction, nf);
+                origin = intersection_point + nf * NEW_RAY_POSITION_OFFSET_DISTANCE;
+            } else {
+                direction = ray.direction * eta + nf * (eta * ci - ct);
+                origin = intersection_point - nf * NEW_RAY_POSITION_OFFSET_DISTANCE;
+            }
+            Ray new_ray = ray_new(origin, direction, ray.max_bounces - 1, ray.original_pixel_pos, ray.spectrum);
+            new_ray.hero = hero;
+            tl_counters.rays_continuation++;
+            submit_ray(new_ray, uniforms);
+            for (size_t i = 0; i < n; ++i)
+                received_spectrum.intensities[i] = (int)i == hero ? new_ray.spectrum.intensities[i] * weight : 0.0f;
+        }
+    } else if (random_z < aabb.material.metallicness) {
         tl_counters.spec_hits++;
         if (ray.max_bounces > 1) {
             V3 reflected_direction = reflect_vec(ray.direction, normal);
@@ -689,6 +742,7 @@ void hit_shader(Ray& ray, const Aabb& aabb, float t, const RaytracingUniforms& u
                                ? reflected_direction
                                : sample_in_cone(reflected_direction, aabb.material.roughness, random_x, random_y);
             Ray new_ray = ray_new(new_shot_rays_pos, direction, ray.max_bounces - 1, ray.original_pixel_pos, ray.spectrum);
+            new_ray.hero = ray.hero;
             tl_counters.rays_continuation++;
             submit_ray(new_ray, uniforms);
             if (new_ray.hit_distance > SPECULAR_MIN_RAY_DISTANCE) add_assign(received_spectrum, new_ray.spectrum);
@@ -713,6 +767,7 @@ void hit_shader(Ray& ray, const Aabb& aabb, float t, const RaytracingUniforms& u
         if (ray.max_bounces > 1) {
             V3 new_direction = global_space_random_bounce_direction(random_x, random_y, normal);
             Ray new_ray = ray_new(intersection_point, new_direction, ray.max_bounces - 1, ray.original_pixel_pos, ray.spectrum);
+            new_ray.hero = ray.hero;
             tl_counters.rays_continuation++;
             submit_ray(new_ray, uniforms);
             max0(new_ray.spectrum);
@@ -865,6 +920,17 @@ void preset_default(Scene& s) {  // main.rs:1638-1758
     default_camera(s);
 }
 
+// BASELINE.json config 3 (extension): the Cornell box plus one dispersive glass sphere.
+void preset_prism(Scene& s) {
+    preset_cornell(s);
+    uint32_t white = add_spectrum(s, new_singular_reflectance_factor(LO, HI, s.n_lambda, 1.0f));
+    uint32_t glass = add_material(s, 0.0f, 0.0f, white);
+    s.materials[glass].transmissive = true;
+    s.materials[glass].ior_a = 1.30f;
+    s.materials[glass].ior_b = 6000.0f;
+    push_obj(s, new_sphere({0.0f, -0.2f, -0.2f}, 0.35f, s.materials[glass]), glass);
+}
+
 // floor + n_spheres spheres placed with the
 // reference's own hash; the two lights of the default scene.
 void preset_spheres(Scene& s, uint32_t n_spheres) {
@@ -999,6 +1065,7 @@ int orc_scene_preset(orc_scene* o, const char* name, uint32_t arg) {
     if (n == "cornell") preset_cornell(o->s);
     else if (n == "default") preset_default(o->s);
     else if (n == "spheres") preset_spheres(o->s, arg);
+    else if (n == "prism") preset_prism(o->s);
     else return -1;
     return 0;
 }
@@ -1012,6 +1079,22 @@ uint32_t orc_scene_add_spectrum(orc_scene* o, const float* v) {
 }
 uint32_t orc_scene_add_material(orc_scene* o, float metallicness, float roughness, uint32_t spectrum_id) {
     return add_material(o->s, metallicness, roughness, spectrum_id);
+}
+uint32_t orc_scene_add_glass(orc_scene* o, uint32_t spectrum_id, float ior_a, float ior_b) {
+    uint32_t m = add_material(o->s, 0.0f, 0.0f, spectrum_id);
+    o->s.materials[m].transmissive = true;
+    o->s.materials[m].ior_a = ior_a;
+    o->s.materials[m].ior_b = ior_b;
+    return m;
+}
+// per material: transmissive (0/1), ior_a, ior_b
+void orc_scene_export_materials_ext(const orc_scene* o, float* out) {
+    for (const Material& m : o->s.materials) {
+        out[0] = m.transmissive ? 1.0f : 0.0f;
+        out[1] = m.ior_a;
+        out[2] = m.ior_b;
+        out += 3;
+    }
 }
 void orc_scene_add_light(orc_scene* o, const float* p, uint32_t spectrum_id) {
     add_light(o->s, {p[0], p[1], p[2]}, spectrum_id);

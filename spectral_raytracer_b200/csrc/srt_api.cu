@@ -700,7 +700,22 @@ int srt_abort(srt_ctx* ctx) {
 int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
     if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
     if (n_frames == 0) return SRT_OK;
-    if (n_frames > kMaxFramesPerCall) return fail(c, SRT_ERR_UNSUPPORTED, "too many frames in one call (max 4194304)");
+    if (n_frames > kMaxFramesPerCall) {  // the per-path state word holds 14 bits of call-relative frame id
+        uint32_t done = 0;
+        float ms = 0.0f;
+        uint64_t launches = 0;
+        while (done < n_frames) {
+            const uint32_t n = std::min(kMaxFramesPerCall, n_frames - done);
+            int rc = srt_render_frames(c, first_frame + done, n);
+            if (rc) return rc;
+            ms += c->last_ms;
+            launches += c->last_launches;
+            done += n;
+        }
+        c->last_ms = ms;
+        c->last_launches = launches;
+        return SRT_OK;
+    }
     DeviceGuard g(c->device);
     if (!g.ok) return fail(c, SRT_ERR_CUDA, "cudaSetDevice failed");
     const unsigned long long total = (unsigned long long)n_frames * c->scene.npix;

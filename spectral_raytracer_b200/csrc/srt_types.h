@@ -84,17 +84,20 @@ struct SceneParams {
     DevObject obj[kMaxConstObjects];
 };
 
-// Path-pool state word (ray_d.w): bits 0..6 remaining bounces (Ray::max_bounces,
-// <= 100 in the UI, main.rs:34), bit 7 parent lobe was specular, bit 8 some
-// ancestor was diffuse (its max0 scrubs NaN, shader.rs:448), bit 9 fresh path
-// (throughput == 1), bits 10..31 frame id relative to the render call.
+// Path-pool state word (ray_d.w): bits 0..6 remaining bounces (Ray::max_bounces, <= 100 in the UI,
+// main.rs:34), bit 7 parent lobe was specular, bit 8 some ancestor was diffuse (its max0 scrubs NaN,
+// shader.rs:448), bit 9 fresh path (throughput == 1), bits 10..17 hero wavelength index + 1 of a path
+// that went through a dispersive interface (0 = full spectrum; extension), bits 18..31 frame id
+// relative to the render call.
 constexpr uint32_t kRemMask = 0x7Fu;
 constexpr uint32_t kFlagPrevSpec = 1u << 7;
 constexpr uint32_t kFlagDiffAncestor = 1u << 8;
 constexpr uint32_t kFlagFresh = 1u << 9;
-constexpr uint32_t kFlagMono = 0;  // (dispersion extension keeps its hero wavelength in a side array)
-constexpr int kFrameShift = 10;
-constexpr uint32_t kMaxFramesPerCall = 1u << (32 - kFrameShift);
+constexpr int kHeroShift = 10;
+constexpr uint32_t kHeroMask = 0xFFu << kHeroShift;
+constexpr int kFrameShift = 18;
+constexpr uint32_t kMaxFramesPerCall = 1u << (32 - kFrameShift);  // larger requests are split by srt_render_frames
+enum : int { kLobeDiffuse = 0, kLobeSpecular = 1, kLobeTransmissive = 2 };
 
 struct PathPool {
     float4* ray_o;  // origin.xyz, w = pixel index (bits)

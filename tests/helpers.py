@@ -6,7 +6,9 @@ import spectral_raytracer_b200 as srt
 
 def flat_from_oracle(oscene) -> srt.FlatScene:
     e = oscene.export()
-    return srt.FlatScene.from_tables(e["n_lambda"], e["camera"], e["objects"], e["materials"], e["lights"])
+    flat = srt.FlatScene.from_tables(e["n_lambda"], e["camera"], e["objects"], e["materials"], e["lights"])
+    flat.materials[:, 3:6] = e["materials_ext"]  # dispersion extension: transmissive, ior_a, ior_b
+    return flat
 
 
 def rel_rmse(a, b):

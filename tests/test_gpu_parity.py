@@ -85,7 +85,7 @@ def _one_frame(r, frame):
 
 @pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
 @pytest.mark.parametrize("name,arg,rng", [("cornell", 0, 0), ("default", 0, 0), ("spheres", 40, 0), ("cornell", 0, 1),
-                                          ("default", 0, 1)])
+                                          ("default", 0, 1), ("prism", 0, 0), ("prism", 0, 1)])
 def test_per_sample_spectra_exact_math(oracle, name, arg, rng, integrator):
     """SRT_MATH_EXACT vs the oracle's canonical-libm mode: every sample's spectrum and every
     event counter must agree (same paths, same hits, same self-hits)."""
@@ -342,3 +342,31 @@ def test_create_rejects_what_the_reference_panics_on(oracle):
     with pytest.raises(srt.SrtError) as e:
         srt.Renderer(dataclasses.replace(flat, objects=objs), 8, 8)
     assert e.value.code == srt.native.SRT_ERR_INVALID_ARGUMENT
+
+
+# --------------------------------------------------------------------------- dispersion extension
+@pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
+def test_prism_extension_converged_and_dispersive(oracle, integrator):
+    """BASELINE.json config 3 has no reference behaviour (the reference has no refraction); parity is against
+    the EXTENDED oracle only.  Production math vs oracle: statistical agreement; and the glass sphere must
+    actually disperse (hero-wavelength paths refract differently per wavelength)."""
+    O = oracle
+    w, h, frames = 128, 72, 64
+    sc = _scene(O, "prism")
+    want = sc.render(w, h, frames, first_frame=0, intended_frames=2 * frames, threads=0)[..., :3]
+    other = sc.render(w, h, frames, first_frame=frames, intended_frames=2 * frames, threads=0)[..., :3]
+    with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=2 * frames, integrator=integrator) as r:
+        r.render_frames(0, frames)
+        got = r.resolve_rgba_f32()[..., :3]
+        ids = r.primary_ids(0, with_t=False)
+    assert np.isfinite(got).all()
+    assert rel_rmse(got, want) <= 0.9 * rel_rmse(other, want)
+    assert abs(got.mean() - want.mean()) / want.mean() <= 0.01
+    glass = ids == ids.max()  # the sphere is the last object
+    assert glass.sum() > 100
+    # inside the sphere's silhouette the image differs from the plain Cornell box
+    plain = _scene(O, "cornell")
+    with srt.Renderer(flat_from_oracle(plain), w, h, intended_frames=2 * frames, integrator=integrator) as r:
+        r.render_frames(0, frames)
+        base = r.resolve_rgba_f32()[..., :3]
+    assert np.abs(got[glass] - base[glass]).mean() > 0.02

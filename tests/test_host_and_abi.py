@@ -40,7 +40,7 @@ def test_abi_struct_sizes_match_header():
 
 
 @pytest.mark.parametrize("name,arg,n_lambda", [("cornell", 0, 32), ("default", 0, 32), ("spheres", 500, 32),
-                                               ("cornell", 0, 64), ("default", 0, 8)])
+                                               ("cornell", 0, 64), ("default", 0, 8), ("prism", 0, 32)])
 def test_host_presets_equal_oracle_scenes(oracle, name, arg, n_lambda):
     """dispatch_render's uniform assembly in the C++ host mirror vs the oracle's restatement of the same
     reference code (main.rs:1389-1404, :1538-1758; shader.rs:108-166): bit-identical inputs."""
@@ -54,10 +54,10 @@ def test_host_presets_equal_oracle_scenes(oracle, name, arg, n_lambda):
     # material / spectrum numbering may differ; compare what each object / light resolves to
     def obj_material(f, i):
         m = f.materials[int(f.objects[i, 22])]
-        return m[0], m[1], f.spectra[int(m[2])]
+        return m[0], m[1], f.spectra[int(m[2])], tuple(m[3:6]) if m[3] else (0,)
     for i in range(len(want.objects)):
         a, b = obj_material(got, i), obj_material(want, i)
-        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2]) and a[3] == b[3]
     assert len(got.lights) == len(want.lights)
     for a, b in zip(got.lights, want.lights):
         assert np.array_equal(a[:3], b[:3])
