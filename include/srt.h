@@ -163,6 +163,8 @@ int srt_set_frames_accumulated(srt_ctx* ctx, uint64_t n_frames);
 /* Device pointer of the accumulation buffer (W*H*n_lambda f32, pixel-major,
  * top-left origin) for zero-copy use by a collective; *n_floats receives its size. */
 void* srt_accum_device_ptr(srt_ctx* ctx, size_t* n_floats);
+/* CUDA device ordinal the context lives on. */
+int srt_device(const srt_ctx* ctx);
 /* The CUDA stream (cudaStream_t) the context launches on. */
 void* srt_stream(srt_ctx* ctx);
 /* Copy the accumulation buffer to / from the host (checkpoint / resume, tests). */

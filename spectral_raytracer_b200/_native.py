@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("SRT_LIB_PATH", os.path.join(_HERE, "libsrt.so"))  # o
 EXPORTS = (
     "srt_abi_version", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
     "srt_render_frames", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
-    "srt_accum_device_ptr", "srt_stream", "srt_read_accum", "srt_write_accum",
+    "srt_accum_device_ptr", "srt_stream", "srt_device", "srt_read_accum", "srt_write_accum",
     "srt_resolve_rgba_f32", "srt_resolve_rgba_u8", "srt_resolve_rgba_f32_device", "srt_primary_ids",
     "srt_spectrum_to_rgb", "srt_get_counters", "srt_reset_counters", "srt_last_render_stats",
     "srt_set_profiling", "srt_last_stage_times",
@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
     L.srt_set_frames_accumulated.argtypes = [vp, u64]
     L.srt_accum_device_ptr.argtypes = [vp, C.POINTER(C.c_size_t)]
     L.srt_accum_device_ptr.restype = vp
+    L.srt_device.argtypes = [vp]
     L.srt_stream.argtypes = [vp]
     L.srt_stream.restype = vp
     L.srt_read_accum.argtypes = [vp, fp]

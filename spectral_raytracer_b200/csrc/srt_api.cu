@@ -818,6 +818,8 @@ void* srt_accum_device_ptr(srt_ctx* c, size_t* n_floats) {
 
 void* srt_stream(srt_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+int srt_device(const srt_ctx* c) { return c ? c->device : -1; }
+
 int srt_read_accum(srt_ctx* c, float* out) {
     if (!c || !out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(c->device);

@@ -199,6 +199,21 @@ class Renderer:
         return [float(x) for x in ms], [int(x) for x in k]
 
 
+def reduce_contexts(renderers) -> None:
+    """srt_reduce (libsrt_nccl.so): sum the accumulation buffers of contexts living on DIFFERENT devices of this
+    process into renderers[0] with NCCL; renderers[0] then holds the whole render."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrt_nccl.so")
+    N.lib()
+    L = C.CDLL(path)
+    L.srt_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
+    L.srt_reduce_last_error.restype = C.c_char_p
+    arr = (C.c_void_p * len(renderers))(*[r._h for r in renderers])
+    rc = L.srt_reduce(arr, len(renderers))
+    if rc != N.SRT_OK:
+        raise N.SrtError(rc, L.srt_reduce_last_error().decode())
+
+
 def spectrum_to_rgb(spectra: np.ndarray, lambda_min: float = 380.0, lambda_max: float = 780.0) -> np.ndarray:
     """Spectrum::get_rgb_early (spectrum.rs:238-261) for a batch of spectra, on the GPU."""
     s = np.ascontiguousarray(spectra, np.float32)

@@ -80,3 +80,25 @@ def test_two_shards_on_one_gpu_equal_one_render():
         a.frames_accumulated = n
         assert np.allclose(a.read_accum(), whole.read_accum(), rtol=1e-5, atol=1e-6)
         assert np.allclose(a.resolve_rgba_f32(), whole.resolve_rgba_f32(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_srt_reduce_nccl_two_devices():
+    """srt_reduce (libsrt_nccl.so): one process, one context per device, NCCL sum onto the first."""
+    import spectral_raytracer_b200 as srt
+    from spectral_raytracer_b200 import scenes
+    from spectral_raytracer_b200.distributed import frame_shard
+    if srt.native.lib().srt_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    flat = scenes.preset("cornell", 32)
+    w, h, n = 160, 90, 6
+    with srt.Renderer(flat, w, h, intended_frames=n, device=0) as whole, \
+            srt.Renderer(flat, w, h, intended_frames=n, device=0) as a, \
+            srt.Renderer(flat, w, h, intended_frames=n, device=1) as b:
+        whole.render_frames(0, n)
+        for rank, r in enumerate((a, b)):
+            first, count = frame_shard(0, n, rank, 2)
+            r.render_frames(first, count)
+        srt.reduce_contexts([a, b])
+        assert a.frames_accumulated == n
+        assert np.allclose(a.resolve_rgba_f32(), whole.resolve_rgba_f32(), rtol=1e-5, atol=1e-6)

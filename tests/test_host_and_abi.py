@@ -27,6 +27,8 @@ def test_library_exports_every_declared_symbol():
     host = scenes.host_lib()
     for name in scenes.HOST_EXPORTS:
         assert hasattr(host, name), name
+    nccl = C.CDLL(os.path.join(ROOT, "spectral_raytracer_b200", "libsrt_nccl.so"))
+    assert hasattr(nccl, "srt_reduce")
 
 
 def test_abi_struct_sizes_match_header():
