@@ -93,7 +93,11 @@ typedef struct srt_camera {
 enum { SRT_RNG_PCG3D_REFERENCE = 0, SRT_RNG_PHILOX = 1 };
 enum { SRT_MATH_FAST = 0, SRT_MATH_EXACT = 1 };
 enum { SRT_ACCEL_AUTO = 0, SRT_ACCEL_LINEAR = 1, SRT_ACCEL_BVH = 2 };
-enum { SRT_INTEGRATOR_WAVEFRONT = 0, SRT_INTEGRATOR_RESIDENT = 1 };
+/* WAVEFRONT: per-stage kernels over SoA path pools in HBM, compaction between bounces.  RESIDENT: one
+ * persistent kernel, a path stays in its lane with its state in registers / shared memory (n_lambda == 32
+ * only, otherwise the wavefront is used).  AUTO: resident for linear-scan scenes, wavefront for BVH scenes
+ * (latency-bound traversal wants the wavefront's higher occupancy). */
+enum { SRT_INTEGRATOR_WAVEFRONT = 0, SRT_INTEGRATOR_RESIDENT = 1, SRT_INTEGRATOR_AUTO = 2 };
 
 /* Per-render constants: RaytracingUniforms minus the scene vectors
  * (shader.rs:32-41) plus the image size (custom_image.rs:18-22) and backend knobs. */

@@ -7,10 +7,10 @@ host mirror of the reference's scene types under host/.  This Python package is
 the ctypes plumbing tests and bench.py use; it contains no rendering code.
 """
 from . import _native as native
-from ._native import (ACCEL_AUTO, ACCEL_BVH, ACCEL_LINEAR, INTEGRATOR_RESIDENT, INTEGRATOR_WAVEFRONT, MATH_EXACT,
+from ._native import (ACCEL_AUTO, ACCEL_BVH, ACCEL_LINEAR, INTEGRATOR_AUTO, INTEGRATOR_RESIDENT, INTEGRATOR_WAVEFRONT, MATH_EXACT,
                       MATH_FAST, RNG_PCG3D_REFERENCE, RNG_PHILOX, SrtError)
 from .renderer import FlatScene, Renderer, reduce_contexts, spectrum_to_rgb
 
 __all__ = ["native", "FlatScene", "Renderer", "spectrum_to_rgb", "reduce_contexts", "SrtError", "ACCEL_AUTO", "ACCEL_BVH",
-           "ACCEL_LINEAR", "INTEGRATOR_RESIDENT", "INTEGRATOR_WAVEFRONT", "MATH_EXACT", "MATH_FAST",
+           "ACCEL_LINEAR", "INTEGRATOR_AUTO", "INTEGRATOR_RESIDENT", "INTEGRATOR_WAVEFRONT", "MATH_EXACT", "MATH_FAST",
            "RNG_PCG3D_REFERENCE", "RNG_PHILOX"]

@@ -30,7 +30,7 @@ PLAIN_BOX, SPHERE, ROTATED_BOX = 0, 1, 2
 RNG_PCG3D_REFERENCE, RNG_PHILOX = 0, 1
 MATH_FAST, MATH_EXACT = 0, 1
 ACCEL_AUTO, ACCEL_LINEAR, ACCEL_BVH = 0, 1, 2
-INTEGRATOR_WAVEFRONT, INTEGRATOR_RESIDENT = 0, 1
+INTEGRATOR_WAVEFRONT, INTEGRATOR_RESIDENT, INTEGRATOR_AUTO = 0, 1, 2
 
 
 class SrtObject(C.Structure):

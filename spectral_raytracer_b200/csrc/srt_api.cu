@@ -656,7 +656,8 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
 
     // integrator: the resident kernel keeps the throughput in registers and is instantiated for the
     // default spectral width (NBR_OF_SPECTRUM_SAMPLES_DEFAULT = 32, main.rs:32); other widths use the wavefront
-    c->resident = params->integrator == SRT_INTEGRATOR_RESIDENT && nl4 == 8;
+    c->resident = nl4 == 8 && (params->integrator == SRT_INTEGRATOR_RESIDENT ||
+                               (params->integrator == SRT_INTEGRATOR_AUTO && !c->use_bvh));
     {
         cudaDeviceProp prop;
         CREATE_TRY(cudaGetDeviceProperties(&prop, device));

@@ -583,7 +583,7 @@ struct RenderOptions {
     uint32_t rng_mode = SRT_RNG_PCG3D_REFERENCE;
     uint32_t math_mode = SRT_MATH_FAST;
     uint32_t accel = SRT_ACCEL_AUTO;
-    uint32_t integrator = SRT_INTEGRATOR_WAVEFRONT;
+    uint32_t integrator = SRT_INTEGRATOR_AUTO;
     int32_t device = -1;
     uint32_t pool_paths = 0;
     uint32_t frames_per_batch = 16;  // progress / abort granularity (the reference polls once per frame, main.rs:1351)

@@ -57,7 +57,7 @@ class Renderer:
 
     def __init__(self, scene: FlatScene, width: int, height: int, *, max_bounces: int = 30,
                  intended_frames: int = 100, rng: int = N.RNG_PCG3D_REFERENCE, math: int = N.MATH_FAST,
-                 accel: int = N.ACCEL_AUTO, integrator: int = N.INTEGRATOR_WAVEFRONT, device: int = -1,
+                 accel: int = N.ACCEL_AUTO, integrator: int = N.INTEGRATOR_AUTO, device: int = -1,
                  pool_paths: int = 0, philox_seed=(0, 0)):
         L = N.lib()
         self._L = L
