@@ -130,6 +130,9 @@ typedef struct srt_counters {
     uint64_t spec_dropped;      /* specular children dropped by the 1e-4 gate (shader.rs:407) */
     uint64_t iterations;        /* wavefront iterations launched                */
     uint64_t kernel_launches;   /* kernels launched by this context             */
+    uint64_t shadow_skipped;    /* shadow rays NOT traced because their light term is exactly zero
+                                   (light behind the surface / surface seen from behind); the reference
+                                   traces them, rays_shadow counts only rays actually traced */
 } srt_counters;
 
 typedef struct srt_ctx srt_ctx;

@@ -63,7 +63,7 @@ class SrtParams(C.Structure):
 class SrtCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
         "samples", "rays_primary", "rays_continuation", "rays_shadow", "hits", "self_hits", "misses", "lit",
-        "spec_hits", "spec_dropped", "iterations", "kernel_launches")]
+        "spec_hits", "spec_dropped", "iterations", "kernel_launches", "shadow_skipped")]
 
 
 class SrtError(RuntimeError):

@@ -939,6 +939,7 @@ int srt_get_counters(srt_ctx* c, srt_counters* out) {
     out->lit = h.v[kCtrLit * kCtrStride];
     out->spec_hits = h.v[kCtrSpecHits * kCtrStride];
     out->spec_dropped = h.v[kCtrSpecDropped * kCtrStride];
+    out->shadow_skipped = h.v[kCtrShadowSkipped * kCtrStride];
     out->iterations = c->iterations;
     out->kernel_launches = c->launches;
     return SRT_OK;

@@ -115,7 +115,7 @@ struct PoolCtl {
 
 enum : int {
     kCtrSamples = 0, kCtrPrimary, kCtrContinuation, kCtrShadow, kCtrHits, kCtrSelfHits,
-    kCtrMisses, kCtrLit, kCtrSpecHits, kCtrSpecDropped, kNumCounters
+    kCtrMisses, kCtrLit, kCtrSpecHits, kCtrSpecDropped, kCtrShadowSkipped, kNumCounters
 };
 constexpr int kCtrStride = 32;  // one counter per 256-byte line
 struct DevCounters {

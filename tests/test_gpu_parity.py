@@ -106,7 +106,10 @@ def test_per_sample_spectra_exact_math(oracle, name, arg, rng, integrator):
             keys = ("samples", "rays_primary")
             if name == "cornell":
                 # ("misses" is not comparable: the oracle's miss_shader also runs for unoccluded shadow rays)
-                keys += ("rays_continuation", "rays_shadow", "hits", "self_hits", "lit", "spec_hits")
+                keys += ("rays_continuation", "hits", "self_hits", "spec_hits")
+                # shadow rays whose light term is exactly zero are not traced (srt_counters.shadow_skipped)
+                assert gc["rays_shadow"] + gc["shadow_skipped"] == oc["rays_shadow"]
+                assert gc["lit"] <= oc["lit"] <= gc["lit"] + gc["shadow_skipped"]
             for k in keys:
                 assert gc[k] == oc[k], (k, gc[k], oc[k])
             both_nan = np.isnan(got) & np.isnan(want)
@@ -194,7 +197,7 @@ def test_bvh_equals_linear_scan(oracle, name, arg):
     a, b = out[srt.ACCEL_LINEAR], out[srt.ACCEL_BVH]
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     assert np.array_equal(a[2], b[2], equal_nan=True)
-    for k in ("hits", "self_hits", "lit", "rays_shadow"):
+    for k in ("hits", "self_hits", "lit", "rays_shadow", "shadow_skipped"):
         assert a[3][k] == b[3][k]
 
 

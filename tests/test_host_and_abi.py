@@ -38,7 +38,7 @@ def test_abi_struct_sizes_match_header():
     assert C.sizeof(srt.native.SrtLight) == 4 * 4
     assert C.sizeof(srt.native.SrtCamera) == 10 * 4
     assert C.sizeof(srt.native.SrtParams) == 15 * 4
-    assert C.sizeof(srt.native.SrtCounters) == 12 * 8
+    assert C.sizeof(srt.native.SrtCounters) == 13 * 8
 
 
 @pytest.mark.parametrize("name,arg,n_lambda", [("cornell", 0, 32), ("default", 0, 32), ("spheres", 500, 32),
