@@ -276,7 +276,7 @@ def main():
     if world > 1:
         dist.all_reduce(e_rank, op=dist.ReduceOp.MAX)
     e2e_value = samples / float(e_rank.item())
-    scene_param_bytes = 13 * 1024  # sizeof(SceneParams), passed by value with every launch
+    scene_param_bytes = int(srt.native.lib().srt_launch_param_bytes())  # sizeof(SceneParams), passed by value with every launch
     h2d = int(e2e_launches / K * scene_param_bytes + 32)
     d2h = int(host_np.nbytes + 32 * max(1, e2e_launches // (3 * K)))
 
@@ -314,9 +314,17 @@ def main():
     bounces_rank0 = counters["rays_primary"] + counters["rays_continuation"]
     alg_bytes = bounces_rank0 * 2 * (32 + 4 * N_LAMBDA + 4 * N_LAMBDA) + counters["lit"] * 4 * N_LAMBDA
     achieved_gbs = alg_bytes / n_launch / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:  # measured DRAM bytes of the dominant kernel (one ncu --set full capture, committed under profiles/)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = "k_resident" if args.integrator == 1 else "k_shade"
+        if key in tr:
+            traffic = tr[key]["dram_bytes_per_sample"] * counters["samples"] / n_launch
+    except OSError:
+        pass
     roofline = {"bound": "hbm", "kernel": "k_resident" if args.integrator == 1 else "k_shade",
                 "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / n_launch, "peak_source": peak_src,
                 "note": "algorithmic bytes = SURVEY 8(d) HBM-resident path state (576 B per path-bounce + 128 B per lit "
                         "event); the resident integrator keeps that state in registers, see roofline_fp32 for the "
                         "bound that applies (north star: FP32 issue rate)"}

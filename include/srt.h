@@ -209,6 +209,9 @@ int srt_reset_counters(srt_ctx* ctx);
  * srt_render_frames call, and the number of kernels it launched. */
 int srt_last_render_stats(srt_ctx* ctx, float* device_ms, uint64_t* kernel_launches);
 
+/* Bytes of the scene block every kernel launch carries host -> device as its parameter (for e2e byte counts). */
+uint32_t srt_launch_param_bytes(void);
+
 /* Optional per-stage timing: when on, CUDA events are recorded around every stage
  * kernel and srt_last_stage_times returns, for the last srt_render_frames call, the
  * summed device time in ms and the launch count of ms[0] ray generation,

@@ -450,6 +450,8 @@ extern "C" {
 
 uint32_t srt_abi_version(void) { return SRT_ABI_VERSION; }
 
+uint32_t srt_launch_param_bytes(void) { return (uint32_t)sizeof(SceneParams); }
+
 int srt_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) {
