@@ -273,6 +273,7 @@ struct srt_ctx {
     float2* mat_params = nullptr;
     float4* mat_ext = nullptr;
     float4* mat_refl = nullptr;
+    int features = 0;  // kFeat* bits: lobes the scene's materials can produce
     DevObject* objects_g = nullptr;
     DevBvhNode* bvh_nodes = nullptr;
     uint32_t* bvh_prims = nullptr;
@@ -360,24 +361,48 @@ void launch_shade_nl(srt_ctx* c, int parity, unsigned long long total, uint32_t 
 template <class Accel>
 void launch_shade(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame, dim3 grid) {
     const bool exact = c->params.math_mode == SRT_MATH_EXACT, philox = c->params.rng_mode == SRT_RNG_PHILOX;
+#ifdef SRT_DEV_MINIMAL  // developer builds for kernel A/B runs: production mode only (compiles in seconds)
+    (void)exact; (void)philox;
+    launch_shade_nl<Accel, false, false>(c, parity, total, first_frame, grid);
+#else
     if (exact && philox) launch_shade_nl<Accel, true, true>(c, parity, total, first_frame, grid);
     else if (exact) launch_shade_nl<Accel, true, false>(c, parity, total, first_frame, grid);
     else if (philox) launch_shade_nl<Accel, false, true>(c, parity, total, first_frame, grid);
     else launch_shade_nl<Accel, false, false>(c, parity, total, first_frame, grid);
+#endif
 }
 
-template <class Accel>
-void launch_resident(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
+template <class Accel, int FEAT>
+void launch_resident_feat(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
     const bool exact = c->params.math_mode == SRT_MATH_EXACT, philox = c->params.rng_mode == SRT_RNG_PHILOX;
     unsigned long long* next = reinterpret_cast<unsigned long long*>(c->ctl);
     float4* acc = reinterpret_cast<float4*>(c->accum);
-#define SRT_RES(E, P) \
-    k_resident<Accel, E, P, 8><<<grid, kResidentBlock, 0, c->stream>>>(c->scene, next, total, first_frame, acc, c->counters)
+    const size_t smem = resident_smem_bytes(c->scene, Accel::kStageInShared, 8);
+#define SRT_RES(E, P)                                                                                                        \
+    do {                                                                                                                     \
+        if (smem > 48 * 1024)                                                                                                \
+            cudaFuncSetAttribute(k_resident<Accel, E, P, 8, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        k_resident<Accel, E, P, 8, FEAT><<<grid, kResidentBlock, smem, c->stream>>>(c->scene, next, total, first_frame, acc, \
+                                                                                  c->counters);                             \
+    } while (0)
+#ifdef SRT_DEV_MINIMAL
+    (void)exact; (void)philox;
+    SRT_RES(false, false);
+#else
     if (exact && philox) SRT_RES(true, true);
     else if (exact) SRT_RES(true, false);
     else if (philox) SRT_RES(false, true);
     else SRT_RES(false, false);
+#endif
 #undef SRT_RES
+}
+// The resident kernel is specialised on the lobes the scene can produce (c->features, kFeat* bits): a
+// Cornell-box-like scene (diffuse only) runs a kernel without the specular / transmissive code.
+template <class Accel>
+void launch_resident(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
+    if (!Accel::kStageInShared || (c->features & kFeatTransmissive)) launch_resident_feat<Accel, kFeatAll>(c, total, first_frame, grid);
+    else if (c->features & kFeatSpecular) launch_resident_feat<Accel, kFeatSpecular>(c, total, first_frame, grid);
+    else launch_resident_feat<Accel, 0>(c, total, first_frame, grid);
 }
 
 // One wavefront iteration: generate -> extend -> shade.  Grids cover the whole
@@ -622,9 +647,11 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
     }
 
     // lights
+    bool tame = true;  // every reflectance in [0,1], every emission in [0,1e18]: no radiance term can be NaN / negative
     for (uint32_t l = 0; l < n_lights; ++l) {
         for (int a = 0; a < 3; ++a) sp.light_pos[l][a] = lights[l].position[a];
         std::memcpy(sp.light_e[l], spectra + (size_t)lights[l].spectrum * nl, nl * sizeof(float));
+        for (uint32_t i = 0; i < nl; ++i) tame = tame && sp.light_e[l][i] >= 0.0f && sp.light_e[l][i] <= 1e18f;
     }
     // materials: reflectance transposed to [n_lambda4][n_materials] float4
     {
@@ -634,8 +661,11 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         std::vector<float4> mr((size_t)nl4 * nm, make_float4(0.f, 0.f, 0.f, 0.f));
         for (uint32_t m = 0; m < n_materials; ++m) {
             mp[m] = make_float2(materials[m].metallicness, materials[m].roughness);
+            if (materials[m].metallicness > 0.0f) c->features |= kFeatSpecular;  // rz in [0,1] < metallicness is possible
+            if (materials[m].transmissive) c->features |= kFeatTransmissive;
             me[m] = make_float4(materials[m].transmissive ? 1.0f : 0.0f, materials[m].ior_a, materials[m].ior_b, 0.0f);
             const float* r = spectra + (size_t)materials[m].reflectance * nl;
+            for (uint32_t i = 0; i < nl; ++i) tame = tame && r[i] >= 0.0f && r[i] <= 1.0f;
             for (uint32_t k = 0; k < nl4; ++k) mr[(size_t)k * n_materials + m] = make_float4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
         }
         CREATE_TRY(cudaMalloc(&c->mat_params, nm * sizeof(float2)));
@@ -647,6 +677,7 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         sp.mat_params = c->mat_params;
         sp.mat_ext = c->mat_ext;
         sp.mat_refl = c->mat_refl;
+        sp.tame = tame ? 1u : 0u;
     }
     // colour weights
     {

@@ -7,7 +7,10 @@
 namespace srt {
 
 constexpr int kMaxLambda = 128;        // spectrum.rs:8  NBR_OF_SAMPLES_MAX
-constexpr int kMaxConstObjects = 64;   // linear-scan scenes live in the kernel-parameter constant bank
+#ifndef SRT_MAX_CONST_OBJECTS
+#define SRT_MAX_CONST_OBJECTS 64
+#endif
+constexpr int kMaxConstObjects = SRT_MAX_CONST_OBJECTS;   // linear-scan scenes live in the kernel-parameter constant bank
 constexpr int kMaxLights = 8;
 constexpr int kBlock = 256;
 
@@ -68,6 +71,7 @@ struct SceneParams {
     uint32_t n_objects, n_lights, n_materials;
     uint32_t n_plain, n_sphere, n_rot;      // primitives are sorted by kind in this order
     uint32_t philox_key[2];
+    uint32_t tame;                          // every reflectance in [0,1], every emission in [0,1e18] (no NaN / negative radiance terms)
     float lambda_min, lambda_step;          // wavelength of sample i = lambda_min + lambda_step * i (dispersion extension)
     // materials (global memory; tiny, L1-resident)
     const float2* mat_params;               // [n_materials] (metallicness, roughness)

@@ -182,15 +182,18 @@ def test_empty_scene_and_no_lights(oracle):
 
 
 # --------------------------------------------------------------------------- BVH == linear scan
+@pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
 @pytest.mark.parametrize("name,arg", [("cornell", 0), ("spheres", 60)])
-def test_bvh_equals_linear_scan(oracle, name, arg):
+def test_bvh_equals_linear_scan(oracle, name, arg, integrator):
+    """Same integrator on both sides: the two differ in how they associate the f32 sum over several lights
+    (per light vs. per pair of lights), the acceleration structures must not differ at all."""
     O = oracle
     w, h, N = 96, 64, 4
     sc = _scene(O, name, 32, arg)
     flat = flat_from_oracle(sc)
     out = {}
     for accel in (srt.ACCEL_LINEAR, srt.ACCEL_BVH):
-        with srt.Renderer(flat, w, h, intended_frames=N, math=srt.MATH_EXACT, accel=accel) as r:
+        with srt.Renderer(flat, w, h, intended_frames=N, math=srt.MATH_EXACT, accel=accel, integrator=integrator) as r:
             ids, t = r.primary_ids(0)
             acc = _one_frame(r, 1)
             out[accel] = (ids, t, acc, r.counters())
