@@ -202,6 +202,12 @@ int srt_primary_ids(srt_ctx* ctx, uint32_t frame, int32_t* ids, float* t);
 int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda,
                         float lambda_min, float lambda_max, float* rgb);
 
+/* Device self-test of the kernels' exact-arithmetic helpers: the batched reciprocal / quotient sequences the
+ * intersection and normalisation code uses instead of one IEEE operation per value are compared bit for bit
+ * with the IEEE operations (1/x, a/b round-to-nearest; what Rust's f32 `/` does, shader.rs:531-556 and
+ * nalgebra's normalize) on n pseudo-random operand sets; *mismatches receives the number of differing results. */
+int srt_selftest_arith(uint64_t n, uint32_t seed, uint64_t* mismatches);
+
 int srt_get_counters(srt_ctx* ctx, srt_counters* out);
 int srt_reset_counters(srt_ctx* ctx);
 

@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SRT_LIB_PATH", os.path.join(_HERE, "libsrt.so"))  # o
 
 # every symbol include/srt.h declares that lives in libsrt.so
 EXPORTS = (
-    "srt_abi_version", "srt_launch_param_bytes", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
+    "srt_abi_version", "srt_launch_param_bytes", "srt_selftest_arith", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
     "srt_render_frames", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
     "srt_accum_device_ptr", "srt_stream", "srt_device", "srt_read_accum", "srt_write_accum",
     "srt_resolve_rgba_f32", "srt_resolve_rgba_u8", "srt_resolve_rgba_f32_device", "srt_primary_ids",
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     fp = C.POINTER(C.c_float)
     L.srt_abi_version.restype = u32
     L.srt_launch_param_bytes.restype = u32
+    L.srt_selftest_arith.argtypes = [u64, u32, C.POINTER(u64)]
     L.srt_device_count.restype = C.c_int
     L.srt_create.argtypes = [C.POINTER(SrtParams), C.POINTER(SrtCamera), C.POINTER(SrtObject), u32,
                              C.POINTER(SrtMaterial), u32, C.POINTER(SrtLight), u32, fp, u32, C.POINTER(vp)]

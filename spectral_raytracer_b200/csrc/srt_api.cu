@@ -956,6 +956,24 @@ int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda, flo
     return SRT_OK;
 }
 
+int srt_selftest_arith(uint64_t n, uint32_t seed, uint64_t* mismatches) {
+    if (!mismatches) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    if (srt_device_count() <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(d, 0, sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+        k_selftest_arith<<<148 * 8, kBlock>>>((unsigned long long)n, seed, d);
+        e = cudaGetLastError();
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, SRT_ERR_CUDA, cudaGetErrorString(e));
+    *mismatches = h;
+    return SRT_OK;
+}
+
 int srt_get_counters(srt_ctx* c, srt_counters* out) {
     if (!c || !out) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(c->device);

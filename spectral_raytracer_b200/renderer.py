@@ -224,3 +224,11 @@ def spectrum_to_rgb(spectra: np.ndarray, lambda_min: float = 380.0, lambda_max: 
                                      lambda_max, out.ctypes.data_as(C.POINTER(C.c_float)))
     N.check(rc, None)
     return out
+
+
+def selftest_arith(n: int = 1 << 26, seed: int = 1) -> int:
+    """srt_selftest_arith: number of results of the kernels' batched exact reciprocal / quotient helpers that
+    differ from the IEEE operations on n pseudo-random operand sets (0 = bit-identical)."""
+    bad = C.c_uint64(0)
+    N.check(N.lib().srt_selftest_arith(n, seed, C.byref(bad)), None)
+    return int(bad.value)

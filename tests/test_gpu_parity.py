@@ -181,6 +181,16 @@ def test_empty_scene_and_no_lights(oracle):
         assert (r.primary_ids(0, with_t=False) == 0).any()
 
 
+# --------------------------------------------------------------------------- exact arithmetic helpers
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [1, 0xC0FFEE])
+def test_batched_reciprocal_and_quotient_are_ieee_exact(seed):
+    """The slab tests need 1/d per axis (shader.rs:531-556) and normalize v/|v| (nalgebra); the kernels compute
+    them three at a time with one range check and a shared reciprocal.  Bit-identical to the IEEE operations
+    on 2^27 pseudo-random operand sets (arbitrary bit patterns, scene-like magnitudes, signed zeros)."""
+    assert srt.selftest_arith(1 << 27, seed) == 0
+
+
 # --------------------------------------------------------------------------- BVH == linear scan
 @pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
 @pytest.mark.parametrize("name,arg", [("cornell", 0), ("spheres", 60)])
