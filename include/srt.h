@@ -158,7 +158,19 @@ const char* srt_last_error(const srt_ctx* ctx);
  * the per-wavelength radiance is ADDED to the accumulation buffer.  Asynchronous
  * w.r.t. the host only inside the call; on return the work is complete. */
 int srt_render_frames(srt_ctx* ctx, uint32_t first_frame, uint32_t n_frames);
-/* Request that a running / the next srt_render_frames stops at a batch boundary. */
+/* App::render's per-frame protocol (main.rs:1338-1357) in batches: after every frames_per_update frames
+ * (0 = 1, the reference's granularity) the callback receives frames_done / frames_total
+ * (AppActions::RenderingProgressUpdate) and, if want_preview, the RGBA8 image of the frames accumulated so far
+ * (AppActions::FrameUpdate, From<CustomImage> for DynamicImage, custom_image.rs:92-101; valid during the call
+ * only); a nonzero return aborts (AppToRenderMessages::AbortRender, polled once per update like try_recv,
+ * main.rs:1351).  The preview is copied out on a second stream while the next batch renders, and the callback
+ * of update k runs while batch k+1 is on the GPU, so an abort takes effect one batch later; frames of completed
+ * batches stay accumulated (srt_frames_accumulated) and the image is consistent.  Returns SRT_ERR_ABORTED when
+ * the render stopped early.  The callback runs on the calling thread. */
+typedef int (*srt_progress_fn)(void* user, uint32_t frames_done, uint32_t frames_total, const uint8_t* rgba8);
+int srt_render_progressive(srt_ctx* ctx, uint32_t first_frame, uint32_t n_frames, uint32_t frames_per_update,
+                           int want_preview, srt_progress_fn callback, void* user);
+/* Request that a running / the next srt_render_frames / srt_render_progressive stops at a batch boundary. */
 int srt_abort(srt_ctx* ctx);
 /* Zero the accumulation buffer and the frame count (a fresh CustomImage::new). */
 int srt_clear(srt_ctx* ctx);

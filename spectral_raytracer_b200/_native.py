@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SRT_LIB_PATH", os.path.join(_HERE, "libsrt.so"))  # o
 # every symbol include/srt.h declares that lives in libsrt.so
 EXPORTS = (
     "srt_abi_version", "srt_launch_param_bytes", "srt_selftest_arith", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
-    "srt_render_frames", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
+    "srt_render_frames", "srt_render_progressive", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
     "srt_accum_device_ptr", "srt_stream", "srt_device", "srt_read_accum", "srt_write_accum",
     "srt_resolve_rgba_f32", "srt_resolve_rgba_u8", "srt_resolve_rgba_f32_device", "srt_primary_ids",
     "srt_spectrum_to_rgb", "srt_get_counters", "srt_reset_counters", "srt_last_render_stats",
@@ -76,6 +76,10 @@ class SrtError(RuntimeError):
 _lib = None
 
 
+# srt_progress_fn
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8))
+
+
 def lib() -> C.CDLL:
     """Load libsrt.so and declare the prototypes.  Raises if the library is missing."""
     global _lib
@@ -90,6 +94,7 @@ def lib() -> C.CDLL:
     fp = C.POINTER(C.c_float)
     L.srt_abi_version.restype = u32
     L.srt_launch_param_bytes.restype = u32
+    L.srt_render_progressive.argtypes = [vp, u32, u32, u32, C.c_int, PROGRESS_FN, vp]
     L.srt_selftest_arith.argtypes = [u64, u32, C.POINTER(u64)]
     L.srt_device_count.restype = C.c_int
     L.srt_create.argtypes = [C.POINTER(SrtParams), C.POINTER(SrtCamera), C.POINTER(SrtObject), u32,

@@ -269,6 +269,11 @@ struct srt_ctx {
     uint32_t weights_used = 0;
     float4* rgba_f32 = nullptr;
     uchar4* rgba_u8 = nullptr;
+    // srt_render_progressive: double-buffered preview (device + pinned host), copy stream, events
+    uchar4* prev_d[2] = {nullptr, nullptr};
+    uint8_t* prev_h[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_resolved[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // scene storage
     float2* mat_params = nullptr;
     float4* mat_ext = nullptr;
@@ -333,6 +338,13 @@ void free_ctx(srt_ctx* c) {
     cudaFree(c->weights);
     cudaFree(c->rgba_f32);
     cudaFree(c->rgba_u8);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->prev_d[i]);
+        if (c->prev_h[i]) cudaFreeHost(c->prev_h[i]);
+        if (c->ev_resolved[i]) cudaEventDestroy(c->ev_resolved[i]);
+        if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     cudaFree(c->mat_params);
     cudaFree(c->mat_ext);
     cudaFree(c->mat_refl);
@@ -731,7 +743,12 @@ int srt_abort(srt_ctx* ctx) {
     return SRT_OK;
 }
 
-int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
+// wait = false (resident integrator only): return once the work is queued on the context's stream
+static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, bool wait);
+
+int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) { return render_frames_impl(c, first_frame, n_frames, true); }
+
+static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, bool wait) {
     if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
     if (n_frames == 0) return SRT_OK;
     if (n_frames > kMaxFramesPerCall) {  // the per-path state word holds 14 bits of call-relative frame id
@@ -740,7 +757,7 @@ int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
         uint64_t launches = 0;
         while (done < n_frames) {
             const uint32_t n = std::min(kMaxFramesPerCall, n_frames - done);
-            int rc = srt_render_frames(c, first_frame + done, n);
+            int rc = render_frames_impl(c, first_frame + done, n, true);
             if (rc) return rc;
             ms += c->last_ms;
             launches += c->last_launches;
@@ -778,11 +795,12 @@ int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
         else launch_resident<AccelLinear>(c, total, first_frame, grid);
         c->launches += 1;
         CUDA_TRY(c, cudaGetLastError());
+        c->last_launches = c->launches - launches_before;
+        c->frames_accumulated += n_frames;
+        if (!wait) return SRT_OK;
         CUDA_TRY(c, cudaEventRecord(c->ev_end, c->stream));
         CUDA_TRY(c, cudaEventSynchronize(c->ev_end));
         CUDA_TRY(c, cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
-        c->last_launches = c->launches - launches_before;
-        c->frames_accumulated += n_frames;
         return SRT_OK;
     }
 
@@ -824,6 +842,91 @@ int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
         return fail(c, SRT_ERR_ABORTED, "render aborted");
     }
     c->frames_accumulated += n_frames;
+    return SRT_OK;
+}
+
+// App::render's per-frame protocol (main.rs:1338-1357) in batches of frames_per_update frames.  Update k's
+// image is resolved to RGBA8 on the render stream, copied to pinned host memory on a second stream while
+// batch k+1 renders, and handed to the callback once the copy is done -- so the GPU never waits for the host,
+// and an abort requested in update k takes effect after batch k+1 (which is already running).
+int srt_render_progressive(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frames_per_update, int want_preview,
+                           srt_progress_fn callback, void* user) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    if (n_frames == 0) return SRT_OK;
+    if (frames_per_update == 0) frames_per_update = 1;  // the reference updates after every frame
+    DeviceGuard g(c->device);
+    if (!g.ok) return fail(c, SRT_ERR_CUDA, "cudaSetDevice failed");
+    const uint32_t npix = c->scene.npix;
+    const bool preview = want_preview && callback;
+    if (preview && !c->copy_stream) {
+        CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(c, cudaMalloc(&c->prev_d[i], (size_t)npix * sizeof(uchar4)));
+            CUDA_TRY(c, cudaMallocHost(&c->prev_h[i], (size_t)npix * 4));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_resolved[i], cudaEventDisableTiming));
+            CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+        }
+    }
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    CUDA_TRY(c, cudaEventCreate(&t0));
+    CUDA_TRY(c, cudaEventCreate(&t1));
+    CUDA_TRY(c, cudaEventRecord(t0, c->stream));
+    const uint64_t launches_before = c->launches;
+    const uint32_t n_updates = (n_frames + frames_per_update - 1) / frames_per_update;
+    bool abort_requested = c->abort_flag != 0;
+    int rc = SRT_OK;
+    uint32_t queued = 0;  // frames queued so far
+    // the callback of update k (frames_done = what batch k completed) fires after batch k+1 was queued
+    auto deliver = [&](uint32_t k, uint32_t frames_done) -> int {
+        const uint8_t* img = nullptr;
+        if (preview) {
+            if (cudaEventSynchronize(c->ev_copied[k & 1]) != cudaSuccess) return -1;
+            img = c->prev_h[k & 1];
+        }
+        return callback ? callback(user, frames_done, n_frames, img) : 0;
+    };
+    uint32_t k = 0;
+    for (; k < n_updates && !abort_requested; ++k) {
+        const uint32_t n = std::min(frames_per_update, n_frames - queued);
+        // resident integrator: queued asynchronously; wavefront: the host drives its iterations, returns when done
+        rc = render_frames_impl(c, first_frame + queued, n, !c->resident);
+        if (rc) break;
+        queued += n;
+        if (preview) {
+            const float frames = c->frames_accumulated ? (float)c->frames_accumulated : 1.0f;
+            k_resolve<<<(npix + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->accum, c->weights, npix, c->scene.n_lambda,
+                                                                              c->weights_used, frames, nullptr, c->prev_d[k & 1]);
+            c->launches += 1;
+            cudaEventRecord(c->ev_resolved[k & 1], c->stream);
+            cudaStreamWaitEvent(c->copy_stream, c->ev_resolved[k & 1], 0);
+            cudaMemcpyAsync(c->prev_h[k & 1], c->prev_d[k & 1], (size_t)npix * 4, cudaMemcpyDeviceToHost, c->copy_stream);
+            cudaEventRecord(c->ev_copied[k & 1], c->copy_stream);
+        }
+        if (k > 0) {
+            const int r = deliver(k - 1, queued - n);
+            if (r < 0) { rc = fail(c, SRT_ERR_CUDA, "preview copy failed"); break; }
+            if (r > 0 || c->abort_flag) abort_requested = true;  // AppToRenderMessages::AbortRender (main.rs:1351-1357)
+        }
+    }
+    // drain: wait for what is in flight, deliver the last update
+    cudaError_t e = cudaEventRecord(t1, c->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(t1);
+    if (rc == SRT_OK && e != cudaSuccess) rc = fail(c, SRT_ERR_CUDA, cudaGetErrorString(e));
+    if (rc == SRT_OK && k > 0) {
+        const int r = deliver(k - 1, queued);
+        if (r < 0) rc = fail(c, SRT_ERR_CUDA, "preview copy failed");
+        else if (r > 0 && queued < n_frames) abort_requested = true;
+    }
+    if (e == cudaSuccess) cudaEventElapsedTime(&c->last_ms, t0, t1);
+    c->last_launches = c->launches - launches_before;
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (rc) return rc;
+    CUDA_TRY(c, cudaGetLastError());
+    if (abort_requested && queued < n_frames) {
+        c->abort_flag = 0;
+        return fail(c, SRT_ERR_ABORTED, "render aborted");
+    }
     return SRT_OK;
 }
 

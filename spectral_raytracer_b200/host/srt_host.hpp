@@ -16,10 +16,13 @@
 // Citations are into /root/reference/src.
 #pragma once
 #include <array>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -668,6 +671,60 @@ inline RenderResult dispatch_render_headless(UIFields& ui, const RenderOptions& 
     ctx.check(srt_resolve_rgba_f32(ctx.h, res.image.data.data()));
     ctx.check(srt_get_counters(ctx.h, &res.counters));
     return res;
+}
+
+// ============================================================== App::render protocol
+// AppActions the render thread pushes for the UI thread (main.rs:1343-1348, :1366-1370) and the message it
+// polls (AppToRenderMessages::AbortRender, main.rs:1351-1357).
+struct AppAction {
+    enum Kind { FrameUpdate, RenderingProgressUpdate, TrueTimeUpdate, DestroySender } kind;
+    std::vector<uint8_t> image;  // FrameUpdate: RGBA8, image_float.clone().into()
+    float progress = 0.0f;       // RenderingProgressUpdate: (frame_number + 1) / nbr_of_iterations
+    double seconds = 0.0;        // TrueTimeUpdate
+};
+struct RenderChannel {
+    std::mutex lock;
+    std::vector<AppAction> action_list;     // Arc<Mutex<Vec<AppActions>>>
+    std::atomic<bool> abort_render{false};  // the Receiver<AppToRenderMessages> side: set to request AbortRender
+    std::atomic<bool> rendering{false};     // Arc<Mutex<bool>> `rendering`
+};
+
+// Sibling of App::render (main.rs:1327-1371) on the GPU: same action sequence -- per update FrameUpdate +
+// RenderingProgressUpdate, abort polled once per update, at the end TrueTimeUpdate + DestroySender -- driven by
+// srt_render_progressive (updates every frames_per_update frames; 1 = the reference's granularity).
+inline bool render(Context& ctx, uint32_t nbr_of_iterations, RenderChannel& ch, uint32_t frames_per_update = 1,
+                   uint32_t first_frame = 0) {
+    ch.rendering = true;
+    const auto begin_time = std::chrono::steady_clock::now();
+    struct Env {
+        Context* ctx;
+        RenderChannel* ch;
+    } env{&ctx, &ch};
+    auto cb = [](void* user, uint32_t done, uint32_t total, const uint8_t* rgba8) -> int {
+        Env* e = static_cast<Env*>(user);
+        {
+            std::lock_guard<std::mutex> g(e->ch->lock);
+            AppAction frame{AppAction::FrameUpdate};
+            if (rgba8) frame.image.assign(rgba8, rgba8 + (size_t)e->ctx->width * e->ctx->height * 4);
+            e->ch->action_list.push_back(std::move(frame));
+            AppAction prog{AppAction::RenderingProgressUpdate};
+            prog.progress = (float)done / (float)total;
+            e->ch->action_list.push_back(std::move(prog));
+        }
+        return e->ch->abort_render.exchange(false) ? 1 : 0;
+    };
+    const int rc = srt_render_progressive(ctx.h, first_frame, nbr_of_iterations, frames_per_update, 1, cb, &env);
+    ch.rendering = false;
+    {
+        std::lock_guard<std::mutex> g(ch.lock);
+        AppAction t{AppAction::TrueTimeUpdate};
+        t.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - begin_time).count();
+        ch.action_list.push_back(std::move(t));
+        ch.action_list.push_back(AppAction{AppAction::DestroySender});
+    }
+    if (rc == SRT_ERR_ABORTED) return false;
+    ctx.check(rc);
+    return true;
 }
 
 }  // namespace srt_host

@@ -1,6 +1,8 @@
 // srt_host_capi.cpp -- extern "C" view of the C++ host mirror (srt_host.hpp) so that the
 // Python plumbing (tests, bench.py) builds its scenes with the product's own builders, and
 // can run the whole headless dispatch in one call.
+#include <thread>
+
 #include "srt_host.hpp"
 
 using namespace srt_host;
@@ -129,6 +131,70 @@ int srth_dispatch_render(const char* preset, uint32_t arg, uint32_t width, uint3
     } catch (const std::exception& e) {
         g_err = e.what();
         return SRT_ERR_INVALID_ARGUMENT;
+    }
+}
+
+// App::render's action protocol for a preset (srt_host::render): runs `iterations` frames with an update every
+// frames_per_update frames; abort_at_update >= 0 sets the AbortRender message while that update's actions are
+// being pushed.  kinds / progress receive the first max_actions entries of the action list (AppAction::Kind,
+// progress value or seconds), last_frame (optional, width*height*4) the image of the last FrameUpdate.
+// Returns the number of actions, or a negative srt status.
+int srth_render_protocol(const char* preset, uint32_t arg, uint32_t width, uint32_t height, uint32_t n_lambda,
+                         uint32_t iterations, uint32_t bounces, uint32_t frames_per_update, int32_t abort_at_update,
+                         int32_t* kinds, float* progress, uint32_t max_actions, uint8_t* last_frame,
+                         uint64_t* frames_accumulated, int32_t* completed) {
+    try {
+        UIFields ui = make_preset(preset, n_lambda, arg);
+        ui.width = width;
+        ui.height = height;
+        ui.nbr_of_iterations = iterations;
+        ui.nbr_of_ray_bounces = bounces;
+        RaytracingUniforms uniforms = build_uniforms(ui);
+        Context ctx(uniforms, width, height, RenderOptions());
+        RenderChannel ch;
+        // the "UI thread": watches the action list and sends AbortRender once update abort_at_update arrived
+        std::atomic<bool> stop{false};
+        std::thread ui_thread([&] {
+            while (!stop) {
+                if (abort_at_update >= 0) {
+                    std::lock_guard<std::mutex> g(ch.lock);
+                    int updates = 0;
+                    for (const AppAction& a : ch.action_list) updates += a.kind == AppAction::RenderingProgressUpdate;
+                    if (updates > abort_at_update) ch.abort_render = true;
+                }
+                std::this_thread::yield();
+            }
+        });
+        bool done = false;
+        try {
+            done = render(ctx, iterations, ch, frames_per_update);
+        } catch (...) {
+            stop = true;
+            ui_thread.join();
+            throw;
+        }
+        stop = true;
+        ui_thread.join();
+        if (completed) *completed = done ? 1 : 0;
+        if (frames_accumulated) *frames_accumulated = srt_frames_accumulated(ctx.h);
+        uint32_t i = 0;
+        const AppAction* last = nullptr;
+        for (const AppAction& a : ch.action_list) {
+            if (i < max_actions) {
+                if (kinds) kinds[i] = (int32_t)a.kind;
+                if (progress) progress[i] = a.kind == AppAction::TrueTimeUpdate ? (float)a.seconds : a.progress;
+            }
+            if (a.kind == AppAction::FrameUpdate) last = &a;
+            ++i;
+        }
+        if (last_frame && last && !last->image.empty()) std::memcpy(last_frame, last->image.data(), last->image.size());
+        return (int)ch.action_list.size();
+    } catch (const SrtError& e) {
+        g_err = e.what();
+        return -e.code;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -SRT_ERR_INVALID_ARGUMENT;
     }
 }
 

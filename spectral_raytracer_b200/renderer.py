@@ -122,6 +122,34 @@ class Renderer:
     def render_frames(self, first_frame: int, n_frames: int):
         N.check(self._L.srt_render_frames(self._h, first_frame, n_frames), self._h)
 
+    def render_progressive(self, first_frame: int, n_frames: int, frames_per_update: int = 1, on_update=None,
+                           preview: bool = False) -> bool:
+        """srt_render_progressive (App::render's FrameUpdate / RenderingProgressUpdate / AbortRender protocol,
+        main.rs:1338-1357).  on_update(frames_done, frames_total, rgba8 or None) -> truthy to abort; the image is
+        an (H, W, 4) uint8 view valid during the callback only.  Returns True when the render was aborted."""
+        errors = []
+
+        def _cb(_user, done, total, img):
+            try:
+                if on_update is None:
+                    return 0
+                arr = None
+                if img:
+                    arr = np.ctypeslib.as_array(img, shape=(self.height, self.width, 4))
+                return 1 if on_update(int(done), int(total), arr) else 0
+            except Exception as e:  # never unwind through the C frames
+                errors.append(e)
+                return 1
+
+        cb = N.PROGRESS_FN(_cb)
+        rc = self._L.srt_render_progressive(self._h, first_frame, n_frames, frames_per_update, 1 if preview else 0, cb, None)
+        if errors:
+            raise errors[0]
+        if rc == N.SRT_ERR_ABORTED:
+            return True
+        N.check(rc, self._h)
+        return False
+
     def clear(self):
         N.check(self._L.srt_clear(self._h), self._h)
 

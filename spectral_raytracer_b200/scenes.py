@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "libsrt_host.so")
 
 HOST_EXPORTS = ("srth_last_error", "srth_scene_preset", "srth_scene_free", "srth_scene_counts", "srth_scene_copy",
-                "srth_spectrum", "srth_black_body", "srth_to_rgba8", "srth_dispatch_render")
+                "srth_spectrum", "srth_black_body", "srth_to_rgba8", "srth_dispatch_render", "srth_render_protocol")
 
 _lib = None
 
@@ -42,6 +42,8 @@ def host_lib() -> C.CDLL:
     L.srth_to_rgba8.argtypes = [fp, C.c_size_t, C.POINTER(C.c_uint8)]
     L.srth_dispatch_render.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, u32, C.c_int32, u32, u32, fp,
                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(N.SrtCounters)]
+    L.srth_render_protocol.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, C.c_int32, C.POINTER(C.c_int32), fp, u32,
+                                       C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -96,3 +98,26 @@ def dispatch_render(preset_name: str, width: int, height: int, iterations: int, 
     info = {"device_seconds": secs.value, "kernel_launches": int(launches.value)}
     info.update({n: int(getattr(ctr, n)) for n, _ in N.SrtCounters._fields_})
     return img, info
+
+
+ACTION_FRAME_UPDATE, ACTION_PROGRESS_UPDATE, ACTION_TRUE_TIME_UPDATE, ACTION_DESTROY_SENDER = range(4)
+
+
+def render_protocol(name: str, width: int, height: int, iterations: int, frames_per_update: int = 1, abort_at_update: int = -1,
+                    n_lambda: int = 32, bounces: int = 30, arg: int = 0):
+    """srt_host::render (the App::render sibling, main.rs:1327-1371) on a preset: returns the action list as
+    (kinds, values), the image of the last FrameUpdate (H, W, 4 uint8), frames accumulated, completed flag."""
+    L = host_lib()
+    cap = 2 * (iterations // max(1, frames_per_update) + 2) + 4
+    kinds = (C.c_int32 * cap)()
+    vals = (C.c_float * cap)()
+    img = np.zeros((height, width, 4), np.uint8)
+    acc = C.c_uint64(0)
+    done = C.c_int32(0)
+    n = L.srth_render_protocol(name.encode(), arg, width, height, n_lambda, iterations, bounces, frames_per_update,
+                               abort_at_update, kinds, vals, cap, img.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(acc),
+                               C.byref(done))
+    if n < 0:
+        raise N.SrtError(-n, L.srth_last_error().decode())
+    n = min(n, cap)
+    return list(kinds[:n]), list(vals[:n]), img, int(acc.value), bool(done.value)
