@@ -214,6 +214,18 @@ int srt_primary_ids(srt_ctx* ctx, uint32_t frame, int32_t* ids, float* t);
 int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda,
                         float lambda_min, float lambda_max, float* rgb);
 
+/* Spectrum tooling on the input side of the path (spectrum.rs:285-374), for n spectra at once, stateless, on the
+ * current CUDA device.
+ *   resample:  Spectrum::resample (spectrum.rs:285-323) from n_old to n_new samples per spectrum (in = n rows of
+ *              n_old floats, out = n rows of n_new).  SRT_ERR_UNSUPPORTED for the reductions the reference panics
+ *              on (a second trip of its down-sampling loop, spectrum.rs:298, or the assert of
+ *              linear_interpolate_halved, spectrum.rs:616 -- e.g. 128 -> 24, 64 -> 8).
+ *   radiance:  Spectrum::get_radiance (spectrum.rs:357-362), sum of I_i * step folded from 0 in sample order.
+ *   normalize: Spectrum::normalize (spectrum.rs:369-374), every sample divided by max(r, g, b) of get_rgb_early. */
+int srt_spectra_resample(const float* in, uint32_t n, uint32_t n_old, uint32_t n_new, float* out);
+int srt_spectra_radiance(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* radiance);
+int srt_spectra_normalize(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* out);
+
 /* Device self-test of the kernels' exact-arithmetic helpers: the batched reciprocal / quotient sequences the
  * intersection and normalisation code uses instead of one IEEE operation per value are compared bit for bit
  * with the IEEE operations (1/x, a/b round-to-nearest; what Rust's f32 `/` does, shader.rs:531-556 and

@@ -69,6 +69,10 @@ def lib():
         L.orc_rgb_loop_count.argtypes = [C.c_uint32, C.c_float, C.c_float]
         L.orc_rgb_loop_count.restype = C.c_uint32
         L.orc_spectrum_build.argtypes = [C.c_uint32, C.c_uint32, C.c_float, C.c_float, fp]
+        L.orc_spectrum_resample.argtypes = [fp, C.c_uint32, C.c_uint32, fp]
+        L.orc_spectrum_radiance.argtypes = [fp, C.c_uint32, C.c_float, C.c_float]
+        L.orc_spectrum_radiance.restype = C.c_float
+        L.orc_spectrum_normalize.argtypes = [fp, C.c_uint32, C.c_float, C.c_float, fp]
         L.orc_euler_rotation.argtypes = [C.c_float, C.c_float, C.c_float, fp]
         L.orc_cosine_direction.argtypes = [C.c_float, C.c_float, fp, fp]
         L.orc_cone_direction.argtypes = [fp, C.c_float, C.c_float, C.c_float, fp]
@@ -236,6 +240,25 @@ def get_rgb_early(intensities, lo=380.0, hi=780.0):
     v = np.ascontiguousarray(intensities, dtype=np.float32)
     o = np.zeros(3, np.float32)
     lib().orc_get_rgb_early(_fp(v), v.shape[0], lo, hi, _fp(o))
+    return o
+
+
+def spectrum_resample(intensities, n_new):
+    """Spectrum::resample (spectrum.rs:285-323); None where the reference panics."""
+    v = np.ascontiguousarray(intensities, dtype=np.float32)
+    o = np.zeros(n_new, np.float32)
+    return None if lib().orc_spectrum_resample(_fp(v), v.shape[0], n_new, _fp(o)) else o
+
+
+def spectrum_radiance(intensities, lo=380.0, hi=780.0):
+    v = np.ascontiguousarray(intensities, dtype=np.float32)
+    return np.float32(lib().orc_spectrum_radiance(_fp(v), v.shape[0], lo, hi))
+
+
+def spectrum_normalize(intensities, lo=380.0, hi=780.0):
+    v = np.ascontiguousarray(intensities, dtype=np.float32)
+    o = np.zeros_like(v)
+    lib().orc_spectrum_normalize(_fp(v), v.shape[0], lo, hi, _fp(o))
     return o
 
 

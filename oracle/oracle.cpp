@@ -1196,6 +1196,87 @@ uint32_t orc_rgb_loop_count(uint32_t n, float lo, float hi) {
     while (wavelength <= hi) { c++; wavelength += sample_distance; }
     return c;
 }
+// ---- Spectrum::resample / get_radiance / normalize (spectrum.rs:285-374, helpers :598-638): the spectrum
+// tooling on the input side of the render path.  Restated literally, including where the
+// reference panics: the down-sampling loop slices working_list[0..self.nbr_of_samples] on every trip
+// (spectrum.rs:298), which is out of range from the second trip on, and linear_interpolate_halved asserts
+// original_length / 2 <= target_length (spectrum.rs:616).  Returns 0 = ok, 1 = the reference panics here.
+static std::vector<float> linear_interpolate_halved(const std::vector<float>& original, size_t target_length, bool& panic) {
+    const size_t original_length = original.size();
+    if (!(original_length > 1 && target_length > 1 && original_length >= target_length && original_length / 2 <= target_length)) {
+        panic = true;
+        return {};
+    }
+    const float factor = (float)original_length / (float)target_length;
+    std::vector<float> result;
+    result.reserve(target_length);
+    for (size_t i = 0; i < target_length; ++i) {
+        const float original_pos = factor * (float)i;
+        const size_t index = (size_t)std::floor(original_pos);
+        const float ratio = original_pos - std::trunc(original_pos);  // f32::fract
+        if (index + 1 < original_length) {
+            const float a = original[index], b = original[index + 1];
+            result.push_back(a * (1.0f - ratio) + b * ratio);
+        } else {
+            result.push_back(original[index]);  // clamp to last value
+        }
+    }
+    return result;
+}
+int orc_spectrum_resample(const float* in, uint32_t n_old, uint32_t n_new, float* out) {
+    if (!(n_new > 1 && n_new <= NBR_OF_SAMPLES_MAX && n_old % 8 == 0 && n_new % 8 == 0 && n_old >= 8 && n_old <= NBR_OF_SAMPLES_MAX)) return 1;
+    if (n_new == n_old) {
+        std::memcpy(out, in, sizeof(float) * n_old);
+        return 0;
+    }
+    if (n_new < n_old) {  // sample down
+        size_t current = n_old;
+        std::vector<float> working(in, in + n_old);
+        bool panic = false;
+        while (current > 2 * (size_t)n_new) {
+            if (working.size() < n_old) return 1;  // &working_list[0..self.nbr_of_samples] out of range
+            // collapse_list_to_half (spectrum.rs:598-607)
+            if (!(working.size() > 8)) return 1;
+            size_t half_length = working.size() / 2;
+            if (half_length % 8 != 0) half_length = (half_length / 8 + 1) * 8;
+            working = linear_interpolate_halved(working, half_length, panic);
+            if (panic) return 1;
+            current = working.size();
+        }
+        working = linear_interpolate_halved(working, n_new, panic);
+        if (panic) return 1;
+        std::memcpy(out, working.data(), sizeof(float) * n_new);
+        return 0;
+    }
+    // up sample (linear interpolation); intensities beyond nbr_of_samples are the zero padding of the [f32; 128]
+    float padded[NBR_OF_SAMPLES_MAX + 1] = {};
+    std::memcpy(padded, in, sizeof(float) * n_old);
+    for (uint32_t i = 0; i < n_new; ++i) {
+        const float index = (float)i / (float)(n_new - 1) * (float)(n_old - 1);
+        const float index_frac = index - std::trunc(index);
+        const size_t index_lower = (size_t)std::floor(index);
+        const size_t index_upper = index_lower + 1;
+        if (index_upper >= NBR_OF_SAMPLES_MAX + 1) return 1;
+        const float frac = 1.0f - index_frac, frac_inv = index_frac;
+        out[i] = padded[index_lower] * frac + padded[index_upper] * frac_inv;
+    }
+    return 0;
+}
+// get_radiance (spectrum.rs:357-362): fold(0, acc + I_i * step), step = (hi - lo) / (n - 1)
+float orc_spectrum_radiance(const float* in, uint32_t n, float lo, float hi) {
+    const float step = (hi - lo) / (float)(n - 1);
+    float acc = 0.0f;
+    for (uint32_t i = 0; i < n; ++i) acc = acc + in[i] * step;
+    return acc;
+}
+// normalize (spectrum.rs:369-374): self / max(r, max(g, b)) of get_rgb_early; Spectrum / f32 divides per sample
+void orc_spectrum_normalize(const float* in, uint32_t n, float lo, float hi, float* out) {
+    float arr[NBR_OF_SAMPLES_MAX] = {};
+    std::memcpy(arr, in, sizeof(float) * n);
+    V3 c = get_rgb_early(new_from_list(arr, lo, hi, n));
+    const float f = std::fmax(c.x, std::fmax(c.y, c.z));  // f32::max
+    for (uint32_t i = 0; i < n; ++i) out[i] = in[i] / f;
+}
 // kind: 0 temperature(arg0=T, arg1=mult) 1 flat(arg0) 2 red(arg0) 3 green(arg0) 4 blue(arg0) 5 sunlight(arg0=mult)
 int orc_spectrum_build(uint32_t kind, uint32_t n, float arg0, float arg1, float* out) {
     Spectrum s;

@@ -9,8 +9,9 @@ the ctypes plumbing tests and bench.py use; it contains no rendering code.
 from . import _native as native
 from ._native import (ACCEL_AUTO, ACCEL_BVH, ACCEL_LINEAR, INTEGRATOR_AUTO, INTEGRATOR_RESIDENT, INTEGRATOR_WAVEFRONT, MATH_EXACT,
                       MATH_FAST, RNG_PCG3D_REFERENCE, RNG_PHILOX, SrtError)
-from .renderer import FlatScene, Renderer, reduce_contexts, selftest_arith, spectrum_to_rgb
+from .renderer import (FlatScene, Renderer, reduce_contexts, selftest_arith, spectra_normalize, spectra_radiance,
+                       spectra_resample, spectrum_to_rgb)
 
-__all__ = ["native", "FlatScene", "Renderer", "spectrum_to_rgb", "selftest_arith", "reduce_contexts", "SrtError", "ACCEL_AUTO", "ACCEL_BVH",
+__all__ = ["native", "FlatScene", "Renderer", "spectrum_to_rgb", "selftest_arith", "spectra_resample", "spectra_radiance", "spectra_normalize", "reduce_contexts", "SrtError", "ACCEL_AUTO", "ACCEL_BVH",
            "ACCEL_LINEAR", "INTEGRATOR_AUTO", "INTEGRATOR_RESIDENT", "INTEGRATOR_WAVEFRONT", "MATH_EXACT", "MATH_FAST",
            "RNG_PCG3D_REFERENCE", "RNG_PHILOX"]

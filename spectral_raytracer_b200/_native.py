@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("SRT_LIB_PATH", os.path.join(_HERE, "libsrt.so"))  # o
 
 # every symbol include/srt.h declares that lives in libsrt.so
 EXPORTS = (
-    "srt_abi_version", "srt_launch_param_bytes", "srt_selftest_arith", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
+    "srt_abi_version", "srt_launch_param_bytes", "srt_selftest_arith", "srt_spectra_resample", "srt_spectra_radiance", "srt_spectra_normalize", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
     "srt_render_frames", "srt_render_progressive", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
     "srt_accum_device_ptr", "srt_stream", "srt_device", "srt_read_accum", "srt_write_accum",
     "srt_resolve_rgba_f32", "srt_resolve_rgba_u8", "srt_resolve_rgba_f32_device", "srt_primary_ids",
@@ -96,6 +96,9 @@ def lib() -> C.CDLL:
     L.srt_launch_param_bytes.restype = u32
     L.srt_render_progressive.argtypes = [vp, u32, u32, u32, C.c_int, PROGRESS_FN, vp]
     L.srt_selftest_arith.argtypes = [u64, u32, C.POINTER(u64)]
+    L.srt_spectra_resample.argtypes = [fp, u32, u32, u32, fp]
+    L.srt_spectra_radiance.argtypes = [fp, u32, u32, C.c_float, C.c_float, fp]
+    L.srt_spectra_normalize.argtypes = [fp, u32, u32, C.c_float, C.c_float, fp]
     L.srt_device_count.restype = C.c_int
     L.srt_create.argtypes = [C.POINTER(SrtParams), C.POINTER(SrtCamera), C.POINTER(SrtObject), u32,
                              C.POINTER(SrtMaterial), u32, C.POINTER(SrtLight), u32, fp, u32, C.POINTER(vp)]

@@ -1059,6 +1059,92 @@ int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda, flo
     return SRT_OK;
 }
 
+// ---- spectrum tooling (spectrum.rs:285-374), stateless, current device
+namespace {
+struct DevBuf {
+    float* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+};
+bool valid_nl(uint32_t nl) { return nl >= 8 && nl % 8 == 0 && nl <= (uint32_t)kMaxLambda; }
+}  // namespace
+
+int srt_spectra_resample(const float* in, uint32_t n, uint32_t n_old, uint32_t n_new, float* out) {
+    if (!in || !out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!valid_nl(n_old) || !valid_nl(n_new))
+        return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
+    // the sizes Spectrum::resample survives: its down-sampling loop may run once (a second trip slices
+    // working_list[0..nbr_of_samples] out of range, spectrum.rs:298) and linear_interpolate_halved needs
+    // original_length / 2 <= target_length (spectrum.rs:616)
+    uint32_t mid = 0;
+    if (n_new < n_old) {
+        uint32_t len = n_old;
+        if (len > 2 * n_new) {
+            mid = len / 2;
+            if (mid % 8 != 0) mid = (mid / 8 + 1) * 8;
+            len = mid;
+            if (len > 2 * n_new) return fail(nullptr, SRT_ERR_UNSUPPORTED, "Spectrum::resample panics for this reduction (spectrum.rs:298)");
+        }
+        if (len / 2 > n_new) return fail(nullptr, SRT_ERR_UNSUPPORTED, "Spectrum::resample panics for this reduction (spectrum.rs:616)");
+    }
+    if (n == 0) return SRT_OK;
+    if (srt_device_count() <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+    DevBuf d_in, d_out;
+    cudaError_t e = cudaMalloc(&d_in.p, (size_t)n * n_old * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out.p, (size_t)n * n_new * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in.p, in, (size_t)n * n_old * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        if (n_new == n_old) e = cudaMemcpy(d_out.p, d_in.p, (size_t)n * n_old * sizeof(float), cudaMemcpyDeviceToDevice);
+        else {
+            k_spectra_resample<<<n, kMaxLambda>>>(d_in.p, n_old, n_new, mid, d_out.p);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out.p, (size_t)n * n_new * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(nullptr, SRT_ERR_CUDA, cudaGetErrorString(e));
+    return SRT_OK;
+}
+
+int srt_spectra_radiance(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* radiance) {
+    if (!in || !radiance) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!valid_nl(n_lambda)) return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
+    if (n == 0) return SRT_OK;
+    if (srt_device_count() <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+    DevBuf d_in, d_out;
+    cudaError_t e = cudaMalloc(&d_in.p, (size_t)n * n_lambda * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out.p, (size_t)n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in.p, in, (size_t)n * n_lambda * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        const float step = (lambda_max - lambda_min) / (float)(n_lambda - 1);  // SpectrumIterator::step, spectrum.rs:328-329
+        k_spectra_radiance<<<(n + kBlock - 1) / kBlock, kBlock>>>(d_in.p, n, n_lambda, step, d_out.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(radiance, d_out.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(nullptr, SRT_ERR_CUDA, cudaGetErrorString(e));
+    return SRT_OK;
+}
+
+int srt_spectra_normalize(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* out) {
+    if (!in || !out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    if (!valid_nl(n_lambda)) return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
+    if (n == 0) return SRT_OK;
+    if (srt_device_count() <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");
+    std::vector<float> w;
+    const uint32_t used = build_rgb_weights(n_lambda, lambda_min, lambda_max, w);
+    DevBuf d_in, d_w, d_out;
+    cudaError_t e = cudaMalloc(&d_in.p, (size_t)n * n_lambda * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_w.p, w.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out.p, (size_t)n * n_lambda * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in.p, in, (size_t)n * n_lambda * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_w.p, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_spectra_normalize<<<(n + kBlock - 1) / kBlock, kBlock>>>(d_in.p, d_w.p, n, n_lambda, used, d_out.p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out.p, (size_t)n * n_lambda * sizeof(float), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return fail(nullptr, SRT_ERR_CUDA, cudaGetErrorString(e));
+    return SRT_OK;
+}
+
 int srt_selftest_arith(uint64_t n, uint32_t seed, uint64_t* mismatches) {
     if (!mismatches) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
     if (srt_device_count() <= 0) return fail(nullptr, SRT_ERR_CUDA, "no CUDA device available (this backend has no CPU fallback)");

@@ -119,6 +119,33 @@ public:
         for (size_t i = 0; i < nbr_of_samples; ++i) intensities[i] = std::fmin(intensities[i], 1.0f);
     }
     size_t get_nbr_of_samples() const { return nbr_of_samples; }
+
+    // The spectrum editor's tooling (spectrum.rs:285-374) runs on the device (srt_spectra_*, include/srt.h):
+    // resample -- a Custom spectrum follows a change of the sample count (main.rs:1193-1195); throws where the
+    // reference panics (reductions beyond what its down-sampling loop survives)
+    void resample(size_t new_sample_amount) {  // :285-323
+        check_samples(new_sample_amount);
+        if (new_sample_amount == nbr_of_samples) return;
+        std::array<float, NBR_OF_SAMPLES_MAX> out{};
+        const int rc = srt_spectra_resample(intensities.data(), 1, (uint32_t)nbr_of_samples, (uint32_t)new_sample_amount, out.data());
+        if (rc != SRT_OK) throw std::runtime_error(srt_last_error(nullptr));
+        intensities = out;
+        nbr_of_samples = new_sample_amount;
+    }
+    float get_radiance() const {  // :357-362
+        float r = 0.0f;
+        if (srt_spectra_radiance(intensities.data(), 1, (uint32_t)nbr_of_samples, lowest_wavelength, highest_wavelength, &r) != SRT_OK)
+            throw std::runtime_error(srt_last_error(nullptr));
+        return r;
+    }
+    Spectrum normalize() const {  // :369-374
+        Spectrum s = *this;
+        s.intensities.fill(0.0f);
+        if (srt_spectra_normalize(intensities.data(), 1, (uint32_t)nbr_of_samples, lowest_wavelength, highest_wavelength,
+                                  s.intensities.data()) != SRT_OK)
+            throw std::runtime_error(srt_last_error(nullptr));
+        return s;
+    }
 };
 
 // ============================================================== nalgebra bits
@@ -252,13 +279,11 @@ struct UISpectrum {
     SpectrumEffectType effect = SpectrumEffectType::Emissive;
     Spectrum spectrum;
 
-    // update_all_spectrum_sample_sizes, main.rs:1186-1228 (Custom spectra would be resampled; the
-    // presets have none, and resample is UI-editor code outside the render path)
+    // update_all_spectrum_sample_sizes, main.rs:1186-1228: Custom spectra are resampled (on the device),
+    // every other kind is rebuilt from its parameters
     void regenerate(float lo, float hi, size_t n) {
         switch (kind) {
-            case UISpectrumKind::Custom:
-                if (spectrum.nbr_of_samples != n) throw std::invalid_argument("custom spectrum has the wrong sample count");
-                break;
+            case UISpectrumKind::Custom: spectrum.resample(n); break;
             case UISpectrumKind::Solar: spectrum = Spectrum::new_sunlight_spectrum(lo, hi, n, arg0); break;
             case UISpectrumKind::PlainReflective: spectrum = Spectrum::new_singular_reflectance_factor(lo, hi, n, arg0); break;
             case UISpectrumKind::Temperature: spectrum = Spectrum::new_temperature_spectrum(lo, hi, arg0, n, arg1); break;

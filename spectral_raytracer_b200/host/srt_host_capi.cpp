@@ -86,6 +86,30 @@ int srth_spectrum(uint32_t kind, uint32_t n, float arg0, float arg1, float* out)
         return -1;
     }
 }
+// Spectrum::resample / get_radiance / normalize through the host mirror's methods (which run on the device):
+// op 0 resample to n_new (out = n_new floats), 1 get_radiance (out[0]), 2 normalize (out = n floats)
+int srth_spectrum_tool(uint32_t op, const float* in, uint32_t n, uint32_t n_new, float* out) {
+    try {
+        std::array<float, NBR_OF_SAMPLES_MAX> a{};
+        std::memcpy(a.data(), in, n * sizeof(float));
+        Spectrum s = Spectrum::new_from_list(a, VISIBLE_LIGHT_WAVELENGTH_LOWER_BOUND, VISIBLE_LIGHT_WAVELENGTH_UPPER_BOUND, n);
+        if (op == 0) {
+            s.resample(n_new);
+            std::memcpy(out, s.intensities.data(), n_new * sizeof(float));
+        } else if (op == 1) {
+            out[0] = s.get_radiance();
+        } else if (op == 2) {
+            Spectrum t = s.normalize();
+            std::memcpy(out, t.intensities.data(), n * sizeof(float));
+        } else {
+            throw std::invalid_argument("unknown spectrum tool");
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
 double srth_black_body(double wavelength_nm, double temperature_k) {
     try {
         return black_body_radiation(wavelength_nm, temperature_k);

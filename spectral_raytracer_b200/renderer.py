@@ -260,3 +260,35 @@ def selftest_arith(n: int = 1 << 26, seed: int = 1) -> int:
     bad = C.c_uint64(0)
     N.check(N.lib().srt_selftest_arith(n, seed, C.byref(bad)), None)
     return int(bad.value)
+
+
+def _rows(spectra):
+    s = np.ascontiguousarray(spectra, np.float32)
+    return s[None, :] if s.ndim == 1 else s
+
+
+def spectra_resample(spectra: np.ndarray, n_new: int) -> np.ndarray:
+    """Spectrum::resample (spectrum.rs:285-323) for a batch of spectra, on the GPU."""
+    s = _rows(spectra)
+    out = np.empty((s.shape[0], n_new), np.float32)
+    N.check(N.lib().srt_spectra_resample(s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], s.shape[1], n_new,
+                                         out.ctypes.data_as(C.POINTER(C.c_float))), None)
+    return out
+
+
+def spectra_radiance(spectra: np.ndarray, lambda_min: float = 380.0, lambda_max: float = 780.0) -> np.ndarray:
+    """Spectrum::get_radiance (spectrum.rs:357-362) for a batch of spectra, on the GPU."""
+    s = _rows(spectra)
+    out = np.empty(s.shape[0], np.float32)
+    N.check(N.lib().srt_spectra_radiance(s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], s.shape[1], lambda_min, lambda_max,
+                                         out.ctypes.data_as(C.POINTER(C.c_float))), None)
+    return out
+
+
+def spectra_normalize(spectra: np.ndarray, lambda_min: float = 380.0, lambda_max: float = 780.0) -> np.ndarray:
+    """Spectrum::normalize (spectrum.rs:369-374) for a batch of spectra, on the GPU."""
+    s = _rows(spectra)
+    out = np.empty_like(s)
+    N.check(N.lib().srt_spectra_normalize(s.ctypes.data_as(C.POINTER(C.c_float)), s.shape[0], s.shape[1], lambda_min, lambda_max,
+                                          out.ctypes.data_as(C.POINTER(C.c_float))), None)
+    return out

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "libsrt_host.so")
 
 HOST_EXPORTS = ("srth_last_error", "srth_scene_preset", "srth_scene_free", "srth_scene_counts", "srth_scene_copy",
-                "srth_spectrum", "srth_black_body", "srth_to_rgba8", "srth_dispatch_render", "srth_render_protocol")
+                "srth_spectrum", "srth_black_body", "srth_to_rgba8", "srth_dispatch_render", "srth_render_protocol", "srth_spectrum_tool")
 
 _lib = None
 
@@ -42,6 +42,7 @@ def host_lib() -> C.CDLL:
     L.srth_to_rgba8.argtypes = [fp, C.c_size_t, C.POINTER(C.c_uint8)]
     L.srth_dispatch_render.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, u32, C.c_int32, u32, u32, fp,
                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(N.SrtCounters)]
+    L.srth_spectrum_tool.argtypes = [u32, fp, u32, u32, fp]
     L.srth_render_protocol.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, C.c_int32, C.POINTER(C.c_int32), fp, u32,
                                        C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
     _lib = L
@@ -121,3 +122,15 @@ def render_protocol(name: str, width: int, height: int, iterations: int, frames_
         raise N.SrtError(-n, L.srth_last_error().decode())
     n = min(n, cap)
     return list(kinds[:n]), list(vals[:n]), img, int(acc.value), bool(done.value)
+
+
+def host_spectrum_tool(op: str, intensities, n_new: int = 0):
+    """Spectrum::resample / get_radiance / normalize as methods of the C++ host mirror (device-backed)."""
+    L = host_lib()
+    v = np.ascontiguousarray(intensities, np.float32)
+    code = {"resample": 0, "radiance": 1, "normalize": 2}[op]
+    out = np.zeros(max(n_new, v.shape[0], 1), np.float32)
+    fp = C.POINTER(C.c_float)
+    if L.srth_spectrum_tool(code, v.ctypes.data_as(fp), v.shape[0], n_new, out.ctypes.data_as(fp)) != 0:
+        raise ValueError(L.srth_last_error().decode())
+    return out[:n_new] if code == 0 else (out[0] if code == 1 else out[:v.shape[0]])

@@ -135,3 +135,42 @@ def test_oracle_scene_statistics(oracle):
     assert 5.0 < c["hits"] / s < 8.0
     assert 0.05 < c["self_hits"] / c["hits"] < 0.25
     assert c["spec_hits"] == 0 and c["rays_shadow"] == c["hits"]
+
+
+# --------------------------------------------------------------------------- spectrum tooling (8f row f3)
+def test_spectrum_resample_restatement(oracle):
+    """Spectrum::resample, spectrum.rs:285-323: identity at equal size, end points kept, flat stays flat, and the
+    reductions the reference panics on (second trip of the down-sampling loop, spectrum.rs:298; assert of
+    linear_interpolate_halved, spectrum.rs:616)."""
+    O = oracle
+    s = O.spectrum(O.SPEC_TEMPERATURE, 32, 6500.0, 1.0)
+    assert np.array_equal(O.spectrum_resample(s, 32), s)
+    up = O.spectrum_resample(s, 64)
+    assert up[0] == s[0] and up[-1] == s[-1] and np.all(np.diff(up[:8]) > 0)
+    # up-sampling: out[i] = I[floor(x)] * (1 - frac) + I[floor(x) + 1] * frac, x = i / (new - 1) * (old - 1)
+    x = np.float32(5) / np.float32(63) * np.float32(31)
+    lo = int(np.floor(x)); fr = np.float32(x - np.trunc(x))
+    assert up[5] == np.float32(s[lo] * (np.float32(1) - fr)) + np.float32(s[lo + 1] * fr)
+    flat = O.spectrum(O.SPEC_FLAT, 128, 0.25)
+    for n in (32, 64, 96):
+        assert np.allclose(O.spectrum_resample(flat, n), 0.25, rtol=1e-6)
+    ok = {(a, b): O.spectrum_resample(O.spectrum(O.SPEC_FLAT, a, 1.0), b) is not None
+          for a in range(8, 129, 8) for b in range(8, 129, 8)}
+    assert all(ok[(a, b)] for a in range(8, 129, 8) for b in range(a, 129, 8))      # up-sampling never panics
+    assert ok[(128, 32)] and ok[(32, 8)] and ok[(64, 16)]                           # one collapse, then interpolate
+    assert not ok[(128, 24)] and not ok[(128, 8)] and not ok[(64, 8)]               # second trip of the loop
+
+
+def test_spectrum_radiance_and_normalize_restatement(oracle):
+    O = oracle
+    flat = O.spectrum(O.SPEC_FLAT, 32, 1.0)
+    step = np.float32(400.0) / np.float32(31)
+    acc = np.float32(0)
+    for _ in range(32):
+        acc = np.float32(acc + step)
+    assert O.spectrum_radiance(flat) == acc                                          # get_radiance, spectrum.rs:357-362
+    for kind, a0, a1 in ((O.SPEC_TEMPERATURE, 6500.0, 1.0), (O.SPEC_TEMPERATURE, 2000.0, 1.0), (O.SPEC_FLAT, 0.7, 0.0)):
+        s = O.spectrum(kind, 32, a0, a1)
+        n = O.spectrum_normalize(s)
+        assert abs(float(O.get_rgb_early(n).max()) - 1.0) < 1e-5                     # spectrum.rs:364-368
+        assert np.allclose(n / n[0], s / s[0], rtol=1e-5)                            # the shape is kept
