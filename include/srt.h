@@ -190,6 +190,19 @@ void* srt_stream(srt_ctx* ctx);
 int srt_read_accum(srt_ctx* ctx, float* out);
 int srt_write_accum(srt_ctx* ctx, const float* in, uint64_t n_frames);
 
+/* The per-render constants a context was created with (device = the ordinal it lives on). */
+int srt_get_params(const srt_ctx* ctx, srt_params* out);
+
+/* Checkpoint / resume.  save writes one file with the scene as given to srt_create, the render constants, the frame
+ * count and the accumulation buffer (FNV-1a checksums; written aside and renamed).  load restores buffer and frame
+ * count into a context of the SAME scene and constants (else SRT_ERR_INVALID_ARGUMENT; accel / integrator / device /
+ * pool size may differ -- they do not change the image).  open builds a new context from the file alone (device = -1:
+ * current device); render further frames with srt_render_frames(ctx, srt_frames_accumulated(ctx), n).
+ * (The reference keeps the image in memory only and lists scene saving as a TODO, main.rs:73.) */
+int srt_checkpoint_save(srt_ctx* ctx, const char* path);
+int srt_checkpoint_load(srt_ctx* ctx, const char* path);
+int srt_checkpoint_open(const char* path, int32_t device, srt_ctx** out);
+
 /* Sum the accumulation buffers of n contexts (one per device, same image size)
  * into ctxs[0] with NCCL (single-process multi-device); ctxs[0]'s frame count
  * becomes the total.  Lives in libsrt_nccl.so. */

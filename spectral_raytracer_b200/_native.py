@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SRT_LIB_PATH", os.path.join(_HERE, "libsrt.so"))  # o
 # every symbol include/srt.h declares that lives in libsrt.so
 EXPORTS = (
     "srt_abi_version", "srt_launch_param_bytes", "srt_selftest_arith", "srt_spectra_resample", "srt_spectra_radiance", "srt_spectra_normalize", "srt_device_count", "srt_create", "srt_destroy", "srt_last_error",
-    "srt_render_frames", "srt_render_progressive", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
+    "srt_render_frames", "srt_render_progressive", "srt_checkpoint_save", "srt_checkpoint_load", "srt_checkpoint_open", "srt_get_params", "srt_abort", "srt_clear", "srt_frames_accumulated", "srt_set_frames_accumulated",
     "srt_accum_device_ptr", "srt_stream", "srt_device", "srt_read_accum", "srt_write_accum",
     "srt_resolve_rgba_f32", "srt_resolve_rgba_u8", "srt_resolve_rgba_f32_device", "srt_primary_ids",
     "srt_spectrum_to_rgb", "srt_get_counters", "srt_reset_counters", "srt_last_render_stats",
@@ -96,6 +96,10 @@ def lib() -> C.CDLL:
     L.srt_launch_param_bytes.restype = u32
     L.srt_render_progressive.argtypes = [vp, u32, u32, u32, C.c_int, PROGRESS_FN, vp]
     L.srt_selftest_arith.argtypes = [u64, u32, C.POINTER(u64)]
+    L.srt_get_params.argtypes = [vp, C.POINTER(SrtParams)]
+    L.srt_checkpoint_save.argtypes = [vp, C.c_char_p]
+    L.srt_checkpoint_load.argtypes = [vp, C.c_char_p]
+    L.srt_checkpoint_open.argtypes = [C.c_char_p, C.c_int32, C.POINTER(vp)]
     L.srt_spectra_resample.argtypes = [fp, u32, u32, u32, fp]
     L.srt_spectra_radiance.argtypes = [fp, u32, u32, C.c_float, C.c_float, fp]
     L.srt_spectra_normalize.argtypes = [fp, u32, u32, C.c_float, C.c_float, fp]

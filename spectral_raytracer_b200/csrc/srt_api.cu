@@ -279,6 +279,13 @@ struct srt_ctx {
     float4* mat_ext = nullptr;
     float4* mat_refl = nullptr;
     int features = 0;  // kFeat* bits: lobes the scene's materials can produce
+    // the scene as handed to srt_create (checkpoint files carry it, srt_checkpoint_open rebuilds the context from it)
+    srt_camera in_camera{};
+    std::vector<srt_object> in_objects;
+    std::vector<srt_material> in_materials;
+    std::vector<srt_light> in_lights;
+    std::vector<float> in_spectra;
+    uint32_t in_n_spectra = 0;
     DevObject* objects_g = nullptr;
     DevBvhNode* bvh_nodes = nullptr;
     uint32_t* bvh_prims = nullptr;
@@ -551,6 +558,12 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
     srt_ctx* c = new srt_ctx();
     c->params = *params;
     c->device = device;
+    c->in_camera = *camera;
+    c->in_objects.assign(objects, objects + n_objects);
+    c->in_materials.assign(materials, materials + n_materials);
+    c->in_lights.assign(lights, lights + n_lights);
+    c->in_spectra.assign(spectra, spectra + (size_t)n_spectra * params->n_lambda);
+    c->in_n_spectra = n_spectra;
     DeviceGuard guard(device);
     if (!guard.ok) {
         delete c;
@@ -971,6 +984,188 @@ int srt_write_accum(srt_ctx* c, const float* in, uint64_t n_frames) {
     CUDA_TRY(c, cudaMemcpyAsync(c->accum, in, c->accum_floats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->frames_accumulated = n_frames;
+    return SRT_OK;
+}
+
+// ---- checkpoint / resume.  One little-endian file:
+//   CkptHeader | srt_params | srt_camera | objects | materials | lights | spectra | accumulation buffer (f32)
+// The scene travels with the image (the reference's own TODO, main.rs:73, is scene serialisation), so a render
+// can be resumed in an existing context (srt_checkpoint_load: scene hash must match) or from the file alone
+// (srt_checkpoint_open).  FNV-1a 64 checksums guard the scene block and the payload.
+namespace {
+struct CkptHeader {
+    char magic[8];  // "SRTCKPT1"
+    uint32_t version, header_bytes;
+    uint32_t width, height, n_lambda;
+    uint32_t n_objects, n_materials, n_lights, n_spectra;
+    uint32_t sizeof_params, sizeof_camera, sizeof_object, sizeof_material, sizeof_light;
+    uint64_t frames_accumulated;
+    uint64_t scene_hash;    // FNV-1a over the scene block (params with device / pool / integrator knobs zeroed .. spectra)
+    uint64_t payload_hash;  // FNV-1a over the accumulation buffer
+    uint64_t payload_floats;
+};
+constexpr uint32_t kCkptVersion = 1;
+uint64_t fnv1a(const void* data, size_t n, uint64_t h = 1469598103934665603ull) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) {
+        h ^= p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+// what defines the IMAGE: backend knobs that do not change the estimator are left out of the hash
+srt_params hashed_params(const srt_params& p) {
+    srt_params q = p;
+    q.accel = 0;
+    q.integrator = 0;
+    q.device = 0;
+    q.pool_paths = 0;
+    return q;
+}
+uint64_t scene_hash_of(const srt_params& p, const srt_camera& cam, const std::vector<srt_object>& o, const std::vector<srt_material>& m,
+                       const std::vector<srt_light>& l, const std::vector<float>& sp) {
+    const srt_params q = hashed_params(p);
+    uint64_t h = fnv1a(&q, sizeof(q));
+    h = fnv1a(&cam, sizeof(cam), h);
+    h = fnv1a(o.data(), o.size() * sizeof(srt_object), h);
+    h = fnv1a(m.data(), m.size() * sizeof(srt_material), h);
+    h = fnv1a(l.data(), l.size() * sizeof(srt_light), h);
+    return fnv1a(sp.data(), sp.size() * sizeof(float), h);
+}
+struct FileCloser {
+    FILE* f;
+    ~FileCloser() { if (f) std::fclose(f); }
+};
+struct CkptFile {
+    CkptHeader h{};
+    srt_params params{};
+    srt_camera camera{};
+    std::vector<srt_object> objects;
+    std::vector<srt_material> materials;
+    std::vector<srt_light> lights;
+    std::vector<float> spectra;
+};
+// reads and validates everything up to the payload; the file position is left at the payload
+int read_ckpt_scene(srt_ctx* c, FILE* f, CkptFile& k) {
+    if (std::fread(&k.h, sizeof(k.h), 1, f) != 1) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: file too short");
+    if (std::memcmp(k.h.magic, "SRTCKPT1", 8) != 0) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: bad magic");
+    if (k.h.version != kCkptVersion || k.h.header_bytes != sizeof(CkptHeader)) return fail(c, SRT_ERR_UNSUPPORTED, "checkpoint: unknown version");
+    if (k.h.sizeof_params != sizeof(srt_params) || k.h.sizeof_camera != sizeof(srt_camera) || k.h.sizeof_object != sizeof(srt_object) ||
+        k.h.sizeof_material != sizeof(srt_material) || k.h.sizeof_light != sizeof(srt_light))
+        return fail(c, SRT_ERR_UNSUPPORTED, "checkpoint: written by a different ABI");
+    if (k.h.n_lambda == 0 || k.h.n_lambda > (uint32_t)kMaxLambda || k.h.n_objects > (1u << 24) || k.h.n_materials > (1u << 24) ||
+        k.h.n_lights > (uint32_t)kMaxLights || k.h.n_spectra > (1u << 24) ||
+        k.h.payload_floats != (uint64_t)k.h.width * k.h.height * k.h.n_lambda)
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: inconsistent header");
+    k.objects.resize(k.h.n_objects);
+    k.materials.resize(k.h.n_materials);
+    k.lights.resize(k.h.n_lights);
+    k.spectra.resize((size_t)k.h.n_spectra * k.h.n_lambda);
+    bool ok = std::fread(&k.params, sizeof(k.params), 1, f) == 1 && std::fread(&k.camera, sizeof(k.camera), 1, f) == 1;
+    ok = ok && std::fread(k.objects.data(), sizeof(srt_object), k.objects.size(), f) == k.objects.size();
+    ok = ok && std::fread(k.materials.data(), sizeof(srt_material), k.materials.size(), f) == k.materials.size();
+    ok = ok && std::fread(k.lights.data(), sizeof(srt_light), k.lights.size(), f) == k.lights.size();
+    ok = ok && std::fread(k.spectra.data(), sizeof(float), k.spectra.size(), f) == k.spectra.size();
+    if (!ok) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: truncated scene block");
+    if (k.params.width != k.h.width || k.params.height != k.h.height || k.params.n_lambda != k.h.n_lambda ||
+        scene_hash_of(k.params, k.camera, k.objects, k.materials, k.lights, k.spectra) != k.h.scene_hash)
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: scene block is corrupt (hash mismatch)");
+    return SRT_OK;
+}
+// reads the payload and uploads it
+int load_ckpt_payload(srt_ctx* c, FILE* f, const CkptHeader& h) {
+    std::vector<float> buf(h.payload_floats);
+    if (std::fread(buf.data(), sizeof(float), buf.size(), f) != buf.size()) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: truncated payload");
+    if (fnv1a(buf.data(), buf.size() * sizeof(float)) != h.payload_hash) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: payload is corrupt (hash mismatch)");
+    return srt_write_accum(c, buf.data(), h.frames_accumulated);
+}
+}  // namespace
+
+int srt_get_params(const srt_ctx* c, srt_params* out) {
+    if (!c || !out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    *out = c->params;
+    out->device = c->device;
+    return SRT_OK;
+}
+
+int srt_checkpoint_save(srt_ctx* c, const char* path) {
+    if (!c || !path) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    std::vector<float> buf(c->accum_floats);
+    int rc = srt_read_accum(c, buf.data());
+    if (rc) return rc;
+    CkptHeader h{};
+    std::memcpy(h.magic, "SRTCKPT1", 8);
+    h.version = kCkptVersion;
+    h.header_bytes = sizeof(CkptHeader);
+    h.width = c->params.width;
+    h.height = c->params.height;
+    h.n_lambda = c->params.n_lambda;
+    h.n_objects = (uint32_t)c->in_objects.size();
+    h.n_materials = (uint32_t)c->in_materials.size();
+    h.n_lights = (uint32_t)c->in_lights.size();
+    h.n_spectra = c->in_n_spectra;
+    h.sizeof_params = sizeof(srt_params);
+    h.sizeof_camera = sizeof(srt_camera);
+    h.sizeof_object = sizeof(srt_object);
+    h.sizeof_material = sizeof(srt_material);
+    h.sizeof_light = sizeof(srt_light);
+    h.frames_accumulated = c->frames_accumulated;
+    h.scene_hash = scene_hash_of(c->params, c->in_camera, c->in_objects, c->in_materials, c->in_lights, c->in_spectra);
+    h.payload_hash = fnv1a(buf.data(), buf.size() * sizeof(float));
+    h.payload_floats = buf.size();
+    const std::string tmp = std::string(path) + ".tmp";  // written aside and renamed: a crash never leaves half a checkpoint
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return fail(c, SRT_ERR_INVALID_ARGUMENT, std::string("checkpoint: cannot open ") + tmp);
+    bool ok = std::fwrite(&h, sizeof(h), 1, f) == 1 && std::fwrite(&c->params, sizeof(srt_params), 1, f) == 1 &&
+              std::fwrite(&c->in_camera, sizeof(srt_camera), 1, f) == 1;
+    ok = ok && std::fwrite(c->in_objects.data(), sizeof(srt_object), c->in_objects.size(), f) == c->in_objects.size();
+    ok = ok && std::fwrite(c->in_materials.data(), sizeof(srt_material), c->in_materials.size(), f) == c->in_materials.size();
+    ok = ok && std::fwrite(c->in_lights.data(), sizeof(srt_light), c->in_lights.size(), f) == c->in_lights.size();
+    ok = ok && std::fwrite(c->in_spectra.data(), sizeof(float), c->in_spectra.size(), f) == c->in_spectra.size();
+    ok = ok && std::fwrite(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok || std::rename(tmp.c_str(), path) != 0) {
+        std::remove(tmp.c_str());
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, std::string("checkpoint: write failed for ") + path);
+    }
+    return SRT_OK;
+}
+
+int srt_checkpoint_load(srt_ctx* c, const char* path) {
+    if (!c || !path) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    FileCloser fc{std::fopen(path, "rb")};
+    if (!fc.f) return fail(c, SRT_ERR_INVALID_ARGUMENT, std::string("checkpoint: cannot open ") + path);
+    CkptFile k;
+    int rc = read_ckpt_scene(c, fc.f, k);
+    if (rc) return rc;
+    if (k.h.width != c->params.width || k.h.height != c->params.height || k.h.n_lambda != c->params.n_lambda)
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: image size / spectral width differ from this context");
+    if (k.h.scene_hash != scene_hash_of(c->params, c->in_camera, c->in_objects, c->in_materials, c->in_lights, c->in_spectra))
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: rendered from a different scene or different render constants");
+    return load_ckpt_payload(c, fc.f, k.h);
+}
+
+int srt_checkpoint_open(const char* path, int32_t device, srt_ctx** out) {
+    if (!out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "out is null");
+    *out = nullptr;
+    if (!path) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
+    FileCloser fc{std::fopen(path, "rb")};
+    if (!fc.f) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, std::string("checkpoint: cannot open ") + path);
+    CkptFile k;
+    int rc = read_ckpt_scene(nullptr, fc.f, k);
+    if (rc) return rc;
+    k.params.device = device;
+    srt_ctx* c = nullptr;
+    rc = srt_create(&k.params, &k.camera, k.objects.data(), (uint32_t)k.objects.size(), k.materials.data(), (uint32_t)k.materials.size(),
+                    k.lights.data(), (uint32_t)k.lights.size(), k.spectra.data(), k.h.n_spectra, &c);
+    if (rc) return rc;
+    rc = load_ckpt_payload(c, fc.f, k.h);
+    if (rc) {
+        const std::string msg = c->error;
+        srt_destroy(c);
+        return fail(nullptr, rc, msg);
+    }
+    *out = c;
     return SRT_OK;
 }
 

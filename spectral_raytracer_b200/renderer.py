@@ -100,6 +100,28 @@ class Renderer:
             raise N.SrtError(rc, msg.decode() if msg else "")
         self._h = h
 
+    @classmethod
+    def open_checkpoint(cls, path: str, device: int = -1) -> "Renderer":
+        """srt_checkpoint_open: a context rebuilt from a checkpoint file alone (scene + accumulated frames)."""
+        L = N.lib()
+        h = C.c_void_p()
+        rc = L.srt_checkpoint_open(str(path).encode(), device, C.byref(h))
+        if rc != N.SRT_OK:
+            msg = L.srt_last_error(None)
+            raise N.SrtError(rc, msg.decode() if msg else "")
+        r = cls.__new__(cls)
+        r._L, r._h, r.scene = L, h, None
+        p = N.SrtParams()
+        N.check(L.srt_get_params(h, C.byref(p)), h)
+        r.width, r.height, r.n_lambda = int(p.width), int(p.height), int(p.n_lambda)
+        return r
+
+    def save_checkpoint(self, path: str):
+        N.check(self._L.srt_checkpoint_save(self._h, str(path).encode()), self._h)
+
+    def load_checkpoint(self, path: str):
+        N.check(self._L.srt_checkpoint_load(self._h, str(path).encode()), self._h)
+
     # ---- life cycle
     def close(self):
         if getattr(self, "_h", None):
