@@ -29,6 +29,17 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version line to stdout when
+# NCCL_DEBUG=VERSION is set in the environment), so everything else is sent to stderr and the JSON line goes to the
+# original stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 WIDTH, HEIGHT, N_LAMBDA, BOUNCES = 1920, 1080, 32, 30
 SCENE = "cornell"
 
@@ -140,7 +151,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world: int, reference: bool = False) -> dict:
@@ -354,7 +365,7 @@ def main():
         "roofline_fp32": fp32,
         "cpu_baseline": cpu,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     r.close()
     if world > 1:
         dist.destroy_process_group()
