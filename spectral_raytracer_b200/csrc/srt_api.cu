@@ -415,13 +415,16 @@ void launch_resident_feat(srt_ctx* c, unsigned long long total, uint32_t first_f
 #endif
 #undef SRT_RES
 }
-// The resident kernel is specialised on the lobes the scene can produce (c->features, kFeat* bits): a
-// Cornell-box-like scene (diffuse only) runs a kernel without the specular / transmissive code.
+// The resident kernel is specialised on what the scene contains (c->features, kFeat* bits: lobes its materials
+// can produce, primitive kinds present): the smallest instantiated superset is launched -- a Cornell-box-like
+// scene (diffuse, plain + rotated boxes) runs a kernel without specular / transmissive / sphere code.
 template <class Accel>
 void launch_resident(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
-    if (!Accel::kStageInShared || (c->features & kFeatTransmissive)) launch_resident_feat<Accel, kFeatAll>(c, total, first_frame, grid);
-    else if (c->features & kFeatSpecular) launch_resident_feat<Accel, kFeatSpecular>(c, total, first_frame, grid);
-    else launch_resident_feat<Accel, 0>(c, total, first_frame, grid);
+    constexpr int kCornellLike = kFeatRot, kDefaultLike = kFeatSpecular | kFeatSphere;
+    const int need = c->features;
+    if (Accel::kStageInShared && (need & ~kCornellLike) == 0) launch_resident_feat<Accel, kCornellLike>(c, total, first_frame, grid);
+    else if (Accel::kStageInShared && (need & ~kDefaultLike) == 0) launch_resident_feat<Accel, kDefaultLike>(c, total, first_frame, grid);
+    else launch_resident_feat<Accel, kFeatAll>(c, total, first_frame, grid);
 }
 
 // One wavefront iteration: generate -> extend -> shade.  Grids cover the whole
@@ -623,7 +626,7 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         return rank(a) < rank(b);
     });
     std::vector<DevObject> dev_objs(n_objects);
-    sp.n_plain = sp.n_sphere = sp.n_rot = 0;
+    sp.n_plain = sp.n_sphere = sp.n_rot = 0;  // (counted below; c->features gets the kinds present)
     for (uint32_t s = 0; s < n_objects; ++s) {
         const srt_object& o = objects[order[s]];
         DevObject& d = dev_objs[s];
@@ -650,6 +653,8 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
             for (int a = 0; a < 9; ++a) d.rot[a] = o.rot[a];
         }
     }
+    if (sp.n_sphere) c->features |= kFeatSphere;
+    if (sp.n_rot) c->features |= kFeatRot;
     c->use_bvh = n_objects > 0 && (params->accel == SRT_ACCEL_BVH ||
                                    (params->accel == SRT_ACCEL_AUTO && n_objects > (uint32_t)kMaxConstObjects));
     if (!c->use_bvh && n_objects > (uint32_t)kMaxConstObjects)
