@@ -386,3 +386,56 @@ def test_prism_extension_converged_and_dispersive(oracle, integrator):
         r.render_frames(0, frames)
         base = r.resolve_rgba_f32()[..., :3]
     assert np.abs(got[glass] - base[glass]).mean() > 0.02
+
+
+# --------------------------------------------------------------------------- more properties at BASELINE's sizes
+@pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
+def test_emission_scaling_is_exactly_linear_full_hd(oracle, integrator):
+    """Radiance is linear in the light's emission spectrum, and scaling by a power of two is exact in f32: one
+    frame at 1920x1080 with E and with 4 E fills accumulation buffers that differ by exactly the factor 4 (one
+    frame, so each pixel's terms are added by one lane in path order; geometry does not depend on E)."""
+    import dataclasses
+    sc = _scene(oracle, "cornell")
+    flat = flat_from_oracle(sc)
+    w, h = 1920, 1080
+    light_spectrum = int(flat.lights[0, 3])
+    spectra4 = flat.spectra.copy()
+    spectra4[light_spectrum] *= np.float32(4.0)
+    with srt.Renderer(flat, w, h, intended_frames=1024, integrator=integrator) as r:
+        r.render_frames(17, 1)
+        base = r.read_accum()
+        c1 = r.counters()
+    with srt.Renderer(dataclasses.replace(flat, spectra=spectra4), w, h, intended_frames=1024, integrator=integrator) as r:
+        r.render_frames(17, 1)
+        scaled = r.read_accum()
+        c4 = r.counters()
+    assert np.array_equal(scaled, base * np.float32(4.0), equal_nan=True)
+    assert base.max() > 0 and np.isfinite(base).all()
+    for k in ("rays_primary", "rays_continuation", "rays_shadow", "hits", "self_hits", "lit"):
+        assert c1[k] == c4[k]
+
+
+def test_frame_shards_add_up_at_4k(oracle):
+    """BASELINE config 4 (3840x2160, frames sharded over the GPUs): two shards of the frame range rendered in
+    separate contexts and summed equal the unsharded render (up to the order of f32 adds), the frame counts add
+    up, and every pixel of the 1.06 GB buffer was written."""
+    sc = _scene(oracle, "cornell")
+    flat = flat_from_oracle(sc)
+    w, h = 3840, 2160
+    with srt.Renderer(flat, w, h, intended_frames=16384) as a:
+        a.render_frames(0, 2)
+        with srt.Renderer(flat, w, h, intended_frames=16384) as b:
+            b.render_frames(2, 1)
+            part = b.read_accum()
+        assert a.counters()["samples"] == 2 * w * h
+        acc = a.read_accum()
+        acc += part
+        a.write_accum(acc, 3)
+        del acc, part
+        sharded = a.resolve_rgba_f32()
+    with srt.Renderer(flat, w, h, intended_frames=16384) as r:
+        r.render_frames(0, 3)
+        whole = r.resolve_rgba_f32()
+        assert r.frames_accumulated == 3
+    assert np.allclose(sharded, whole, rtol=1e-5, atol=1e-7)
+    assert np.isfinite(whole).all() and (whole[..., :3].max(axis=2) > 0).mean() > 0.9   # (the box does not fill the frame)
