@@ -155,11 +155,12 @@ void build_bvh(const std::vector<DevObject>& objs, std::vector<DevBvhNode>& node
             nodes[t.node].left_or_first = t.first;
             nodes[t.node].count = t.count;
         };
-        if (t.count <= kLeaf || t.depth >= 40) {
-            if (t.count <= 64 || t.depth >= 44) {
-                make_leaf();
-                continue;
-            }
+        // leaves hold at most 64 primitives (the traversal packs the count into 8 bits); from depth 40 on the
+        // tree is finished with median splits, so it is never deeper than 40 + log2(2^24 / 64) = 58 < kBvhStack
+        const bool deep = t.depth >= 40;
+        if (t.count <= kLeaf || (deep && t.count <= 64)) {
+            make_leaf();
+            continue;
         }
         // binned SAH over the centroid bounds
         int best_axis = -1, best_split = -1;
@@ -168,7 +169,7 @@ void build_bvh(const std::vector<DevObject>& objs, std::vector<DevBvhNode>& node
             float dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
             return 2.0f * (dx * dy + dy * dz + dz * dx);
         };
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < 3 && !deep; ++a) {
             float ext = cmx[a] - cmn[a];
             if (!(ext > 0.0f)) continue;
             struct Bin {
