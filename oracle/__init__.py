@@ -84,6 +84,8 @@ def lib():
         L.orc_primary.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), fp,
                                   C.POINTER(C.c_uint8)]
         L.orc_counters_get.argtypes = [C.POINTER(C.c_uint64)]
+        L.orc_render_pixels.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, fp,
+                                        C.c_int]
         L.orc_set_modes.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32]
         L.orc_hardware_threads.restype = C.c_uint
         _lib = L
@@ -186,6 +188,14 @@ class Scene:
         depth = C.c_uint32()
         lib().orc_sample(self._h, w, h, max_bounces, x, y, frame, intended_frames, _fp(spec), _fp(rgb), C.byref(depth))
         return spec, rgb, depth.value
+
+    def render_pixels(self, w, h, xy, n_frames, max_bounces=30, threads=0):
+        """The frame loop for a subset of the pixels of a w x h image: (n, 4) f32 running means."""
+        xy = np.ascontiguousarray(xy, np.uint32)
+        out = np.zeros((xy.shape[0], 4), np.float32)
+        lib().orc_render_pixels(self._h, w, h, max_bounces, n_frames, xy.ctypes.data_as(C.POINTER(C.c_uint32)), xy.shape[0],
+                                _fp(out), threads)
+        return out
 
     def primary(self, w, h, frame=0, intended_frames=1):
         ids = np.zeros((h, w), np.int32)

@@ -12,7 +12,10 @@ constexpr int kMaxLambda = 128;        // spectrum.rs:8  NBR_OF_SAMPLES_MAX
 #endif
 constexpr int kMaxConstObjects = SRT_MAX_CONST_OBJECTS;   // linear-scan scenes live in the kernel-parameter constant bank
 constexpr int kMaxLights = 8;
-constexpr int kBlock = 256;
+#ifndef SRT_BLOCK
+#define SRT_BLOCK 256
+#endif
+constexpr int kBlock = SRT_BLOCK;
 
 constexpr float kF32Delta = 0.00001f;          // shader.rs:7
 constexpr float kNewRayOffset = 0.00001f;      // shader.rs:8
