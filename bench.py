@@ -110,7 +110,8 @@ class ClockSampler:
 
 def cpu_reference_run(n_frames: int, threads: int, first_frame: int = 0, counters: bool = False):
     """The reference's CPU path (oracle/oracle.cpp, platform libm, row-per-task pool) on n_frames of the
-    bench workload.  Returns (seconds, samples, counters|None).  The oracle is only ever the baseline here."""
+    bench workload.  Returns (seconds, samples, counters|None, image).  The oracle is only ever the baseline / the
+    checker here."""
     import oracle as O
     O.build()
     O.set_modes(O.MATH_NATIVE, O.RNG_PCG3D)
@@ -118,10 +119,10 @@ def cpu_reference_run(n_frames: int, threads: int, first_frame: int = 0, counter
     if counters:
         O.counters_reset()
     t0 = time.perf_counter()
-    sc.render(WIDTH, HEIGHT, n_frames, first_frame=first_frame, intended_frames=1024, max_bounces=BOUNCES,
-              threads=threads)
+    img = sc.render(WIDTH, HEIGHT, n_frames, first_frame=first_frame, intended_frames=1024, max_bounces=BOUNCES,
+                    threads=threads)
     dt = time.perf_counter() - t0
-    return dt, n_frames * WIDTH * HEIGHT, (O.counters() if counters else None)
+    return dt, n_frames * WIDTH * HEIGHT, (O.counters() if counters else None), img
 
 
 def run_reference(args, rank: int, world: int):
@@ -136,7 +137,7 @@ def run_reference(args, rank: int, world: int):
     t = 0.0
     samples = 0
     for k in range(args.steps):
-        dt, n, _ = cpu_reference_run(1, threads, first_frame=args.warmup + k)
+        dt, n, _, _ = cpu_reference_run(1, threads, first_frame=args.warmup + k)
         t += dt
         samples += n
     value = samples / t
@@ -294,12 +295,34 @@ def main():
     # ---------------- CPU baseline (rank 0, N=1): bounded sample of the same workload
     cpu = None
     oc = None
+    rmse = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle as O
         threads = O.hardware_threads()
-        dt, n, oc = cpu_reference_run(1, threads, counters=True)
+        dt, n, oc, _ = cpu_reference_run(1, threads, counters=True)
         frames = int(min(24, max(1, 12.0 / dt)))
-        dt2, n2, _ = cpu_reference_run(frames, threads, first_frame=1)
+        dt2, n2, _, cpu_img = cpu_reference_run(frames, threads, first_frame=1)
+        # (the reference blends frame f with ratio 1 / (f + 1), custom_image.rs:71-76: started at frame 1 on an empty image the
+        # running mean counts an all-zero frame 0 -- undo that to get the mean of the frames actually rendered)
+        cpu_img = cpu_img * np.float32((frames + 1) / frames)
+        # RMSE vs the CPU reference (BASELINE.json's metric): the same frames on the GPU, production settings, against
+        # the image the CPU baseline just rendered; relative RMSE on linear f32 RGB (SURVEY 8d gate 3).  The noise floor
+        # beside it is the same statistic for DISJOINT frames (what two independent estimates of this length differ by).
+        def rel_rmse(a, b):
+            ok = np.isfinite(a).all(axis=2) & np.isfinite(b).all(axis=2)
+            a, b = a[ok].astype(np.float64), b[ok].astype(np.float64)
+            return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
+        with srt.Renderer(flat, WIDTH, HEIGHT, intended_frames=1024, max_bounces=BOUNCES, integrator=args.integrator,
+                          device=local_rank) as rr:
+            rr.render_frames(1, frames)
+            same = rr.resolve_rgba_f32()[..., :3]
+            rr.clear()
+            rr.render_frames(1 + frames, frames)
+            other = rr.resolve_rgba_f32()[..., :3]
+        rmse = {"rel_rmse_vs_cpu": rel_rmse(same, cpu_img[..., :3]), "noise_floor": rel_rmse(other, cpu_img[..., :3]),
+                "mean_ratio": float(np.nanmean(same) / np.nanmean(cpu_img[..., :3])), "frames": frames,
+                "what": "1920x1080 Cornell box, the same frame ids on the GPU (production math) and on the CPU reference port; "
+                        "relative RMSE of linear RGB; noise_floor = disjoint frame ids"}
         cpu = {"value": (n + n2) / (dt + dt2), "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"{frames + 1} frames of the same 1920x1080 Cornell box ({(n + n2) / 1e6:.1f} M samples, "
                          f"{dt + dt2:.1f} s), C++ restatement of the Rust reference with its cost structure "
@@ -364,6 +387,7 @@ def main():
         "roofline": roofline,
         "roofline_fp32": fp32,
         "cpu_baseline": cpu,
+        "rmse": rmse,
     }
     emit(line)
     r.close()
