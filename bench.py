@@ -343,10 +343,15 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     n_launch = max(1, launches if args.integrator == 1 else stage_n[2])
     kernel_ms = (render_ms if args.integrator == 1 else stage_ms[2]) / n_launch
-    # algorithmic bytes: 576 B of path state per path-bounce (ray 32 B + throughput 4*n_lambda +
-    # radiance 4*n_lambda, read and written) + 4*n_lambda per accumulation write, from THIS run's counters (rank 0)
+    # Algorithmic HBM bytes, from THIS run's counters (rank 0).
+    #  * SURVEY.md 8(d), wavefront with HBM-resident path state: 576 B per path-bounce (ray 32 B + throughput 4*n_lambda +
+    #    radiance 4*n_lambda, read and written) + 4*n_lambda per accumulation write.  That is what the WAVEFRONT moves.
+    #  * the RESIDENT integrator keeps ray and throughput on chip; what it must move is the accumulation buffer, which
+    #    is larger than L2 and whose every pixel record (4*n_lambda B) is read and written once per frame.
     bounces_rank0 = counters["rays_primary"] + counters["rays_continuation"]
-    alg_bytes = bounces_rank0 * 2 * (32 + 4 * N_LAMBDA + 4 * N_LAMBDA) + counters["lit"] * 4 * N_LAMBDA
+    state_bytes = bounces_rank0 * 2 * (32 + 4 * N_LAMBDA + 4 * N_LAMBDA) + counters["lit"] * 4 * N_LAMBDA
+    accum_bytes = counters["samples"] * 2 * 4 * N_LAMBDA
+    alg_bytes = accum_bytes if args.integrator == 1 else state_bytes
     achieved_gbs = alg_bytes / n_launch / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:  # measured DRAM bytes of the dominant kernel (one ncu --set full capture, committed under profiles/)
@@ -359,9 +364,14 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_resident" if args.integrator == 1 else "k_shade",
                 "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / n_launch, "peak_source": peak_src,
-                "note": "algorithmic bytes = SURVEY 8(d) HBM-resident path state (576 B per path-bounce + 128 B per lit "
-                        "event); the resident integrator keeps that state in registers, see roofline_fp32 for the "
-                        "bound that applies (north star: FP32 issue rate)"}
+                "algorithmic_bytes_per_sample": alg_bytes / max(1, counters["samples"]),
+                "survey_8d_hbm_resident_state_bytes_per_sample": state_bytes / max(1, counters["samples"]),
+                "note": ("resident integrator: path state stays on chip, the algorithmic HBM traffic is the accumulation buffer "
+                         "(one 128-byte pixel record read + written per sample); the kernel is bound by instruction issue, see "
+                         "roofline_fp32 (north star: FP32 issue rate).  SURVEY 8(d)'s figure for an HBM-resident wavefront state "
+                         "is given beside it: at this throughput it would need more than the HBM peak."
+                         if args.integrator == 1 else
+                         "wavefront: SURVEY 8(d) HBM-resident path state, 576 B per path-bounce + 128 B per lit event")}
     sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     fp32 = None
     if oc is not None:
