@@ -20,23 +20,28 @@ COUNTER_NAMES = (
 )
 
 
+_TIGHT_LIB_PATH = os.path.join(_HERE, "liboracle_tight.so")
+
+
 def build(force: bool = False) -> str:
-    """Compile oracle.cpp -> liboracle.so with the committed Makefile."""
+    """Compile oracle.cpp -> liboracle.so (faithful cost structure) and liboracle_tight.so (-DORACLE_TIGHT: same
+    arithmetic, the reference's avoidable cost items removed) with the committed Makefile."""
     src = os.path.join(_HERE, "oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    stale = [p for p in (_LIB_PATH, _TIGHT_LIB_PATH) if not os.path.exists(p) or os.path.getmtime(p) < os.path.getmtime(src)]
+    if force or stale:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        if not os.path.exists(_LIB_PATH):
+def lib(tight: bool = False):
+    if tight not in _libs:
+        path = _TIGHT_LIB_PATH if tight else _LIB_PATH
+        if not os.path.exists(path):
             build()
-        L = C.CDLL(_LIB_PATH)
+        L = C.CDLL(path)
         fp = C.POINTER(C.c_float)
         L.orc_scene_new.restype = C.c_void_p
         L.orc_scene_new.argtypes = [C.c_uint32]
@@ -88,8 +93,9 @@ def lib():
                                         C.c_int]
         L.orc_set_modes.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32]
         L.orc_hardware_threads.restype = C.c_uint
-        _lib = L
-    return _lib
+        assert bool(L.orc_is_tight()) == tight
+        _libs[tight] = L
+    return _libs[tight]
 
 
 def _fp(a: np.ndarray):
@@ -104,67 +110,68 @@ def _f3(v):
 class Scene:
     """Opaque oracle scene (RaytracingUniforms + the spectra/material tables)."""
 
-    def __init__(self, n_lambda: int = 32, preset: str | None = None, arg: int = 0):
+    def __init__(self, n_lambda: int = 32, preset: str | None = None, arg: int = 0, tight: bool = False):
         self.n_lambda = n_lambda
-        self._h = lib().orc_scene_new(n_lambda)
+        self._L = lib(tight)
+        self._h = self._L.orc_scene_new(n_lambda)
         if not self._h:
             raise ValueError("illegal number of spectral samples (multiple of 8, <= 128)")
         if preset is not None:
-            if lib().orc_scene_preset(self._h, preset.encode(), arg) != 0:
+            if self._L.orc_scene_preset(self._h, preset.encode(), arg) != 0:
                 raise ValueError(f"unknown preset {preset}")
 
     def __del__(self):
         if getattr(self, "_h", None):
-            lib().orc_scene_free(self._h)
+            self._L.orc_scene_free(self._h)
             self._h = None
 
     # ---- building
     def set_camera(self, pos, direction, up, fov_y_deg):
-        lib().orc_scene_set_camera(self._h, _f3(pos), _f3(direction), _f3(up), fov_y_deg)
+        self._L.orc_scene_set_camera(self._h, _f3(pos), _f3(direction), _f3(up), fov_y_deg)
 
     def add_spectrum(self, values) -> int:
         v = np.ascontiguousarray(values, dtype=np.float32)
         assert v.shape == (self.n_lambda,)
-        return lib().orc_scene_add_spectrum(self._h, _fp(v))
+        return self._L.orc_scene_add_spectrum(self._h, _fp(v))
 
     def add_material(self, metallicness, roughness, spectrum_id) -> int:
-        return lib().orc_scene_add_material(self._h, metallicness, roughness, spectrum_id)
+        return self._L.orc_scene_add_material(self._h, metallicness, roughness, spectrum_id)
 
     def add_glass(self, spectrum_id, ior_a, ior_b) -> int:
         """extension: dispersive dielectric, n(lambda) = ior_a + ior_b / lambda_nm^2"""
-        return lib().orc_scene_add_glass(self._h, spectrum_id, ior_a, ior_b)
+        return self._L.orc_scene_add_glass(self._h, spectrum_id, ior_a, ior_b)
 
     def add_light(self, pos, spectrum_id):
-        lib().orc_scene_add_light(self._h, _f3(pos), spectrum_id)
+        self._L.orc_scene_add_light(self._h, _f3(pos), spectrum_id)
 
     def add_sphere(self, center, radius, material):
-        lib().orc_scene_add_sphere(self._h, _f3(center), radius, material)
+        self._L.orc_scene_add_sphere(self._h, _f3(center), radius, material)
 
     def add_box(self, center, lengths, material):
-        lib().orc_scene_add_box(self._h, _f3(center), _f3(lengths), material)
+        self._L.orc_scene_add_box(self._h, _f3(center), _f3(lengths), material)
 
     def add_rotated_box(self, center, lengths, euler, material):
-        lib().orc_scene_add_rotated_box(self._h, _f3(center), _f3(lengths), _f3(euler), material)
+        self._L.orc_scene_add_rotated_box(self._h, _f3(center), _f3(lengths), _f3(euler), material)
 
     # ---- export
     def export(self) -> dict:
         n = [C.c_uint32() for _ in range(4)]
-        nl = lib().orc_scene_counts(self._h, *[C.byref(x) for x in n])
+        nl = self._L.orc_scene_counts(self._h, *[C.byref(x) for x in n])
         n_obj, n_mat, n_light, n_spec = [x.value for x in n]
         obj = np.zeros((n_obj, 26), np.float32)
         mat = np.zeros((n_mat, 2 + nl), np.float32)
         lig = np.zeros((n_light, 3 + nl), np.float32)
         cam = np.zeros(10, np.float32)
         if n_obj:
-            lib().orc_scene_export_objects(self._h, _fp(obj))
+            self._L.orc_scene_export_objects(self._h, _fp(obj))
         if n_mat:
-            lib().orc_scene_export_materials(self._h, _fp(mat))
+            self._L.orc_scene_export_materials(self._h, _fp(mat))
         if n_light:
-            lib().orc_scene_export_lights(self._h, _fp(lig))
-        lib().orc_scene_export_camera(self._h, _fp(cam))
+            self._L.orc_scene_export_lights(self._h, _fp(lig))
+        self._L.orc_scene_export_camera(self._h, _fp(cam))
         ext = np.zeros((n_mat, 3), np.float32)
         if n_mat:
-            lib().orc_scene_export_materials_ext(self._h, _fp(ext))
+            self._L.orc_scene_export_materials_ext(self._h, _fp(ext))
         return {"n_lambda": nl, "objects": obj, "materials": mat, "lights": lig, "camera": cam, "materials_ext": ext}
 
     # ---- rendering
@@ -177,7 +184,7 @@ class Scene:
         if img is None:
             img = np.zeros((h, w, 4), np.float32)
         spec = np.zeros((h, w, self.n_lambda), np.float64) if spectral else None
-        rc = lib().orc_render(self._h, w, h, max_bounces, first_frame, n_frames, intended_frames, threads, _fp(img),
+        rc = self._L.orc_render(self._h, w, h, max_bounces, first_frame, n_frames, intended_frames, threads, _fp(img),
                               spec.ctypes.data_as(C.POINTER(C.c_double)) if spectral else None)
         assert rc == 0
         return (img, spec) if spectral else img
@@ -186,14 +193,14 @@ class Scene:
         spec = np.zeros(self.n_lambda, np.float32)
         rgb = np.zeros(3, np.float32)
         depth = C.c_uint32()
-        lib().orc_sample(self._h, w, h, max_bounces, x, y, frame, intended_frames, _fp(spec), _fp(rgb), C.byref(depth))
+        self._L.orc_sample(self._h, w, h, max_bounces, x, y, frame, intended_frames, _fp(spec), _fp(rgb), C.byref(depth))
         return spec, rgb, depth.value
 
     def render_pixels(self, w, h, xy, n_frames, max_bounces=30, threads=0):
         """The frame loop for a subset of the pixels of a w x h image: (n, 4) f32 running means."""
         xy = np.ascontiguousarray(xy, np.uint32)
         out = np.zeros((xy.shape[0], 4), np.float32)
-        lib().orc_render_pixels(self._h, w, h, max_bounces, n_frames, xy.ctypes.data_as(C.POINTER(C.c_uint32)), xy.shape[0],
+        self._L.orc_render_pixels(self._h, w, h, max_bounces, n_frames, xy.ctypes.data_as(C.POINTER(C.c_uint32)), xy.shape[0],
                                 _fp(out), threads)
         return out
 
@@ -201,7 +208,7 @@ class Scene:
         ids = np.zeros((h, w), np.int32)
         t = np.zeros((h, w), np.float32)
         band = np.zeros((h, w), np.uint8)
-        lib().orc_primary(self._h, w, h, frame, intended_frames, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(t),
+        self._L.orc_primary(self._h, w, h, frame, intended_frames, ids.ctypes.data_as(C.POINTER(C.c_int32)), _fp(t),
                           band.ctypes.data_as(C.POINTER(C.c_uint8)))
         return ids, t, band
 
@@ -214,6 +221,8 @@ def set_modes(math_mode=MATH_NATIVE, rng_mode=RNG_PCG3D, philox_key=(0, 0)):
     """Process-wide oracle modes (see oracle.cpp, g_math_mode): math 0 = platform f32 libm
     (what the reference calls), 1 = correctly rounded; rng 0 = pcg3d (reference), 1 = Philox."""
     lib().orc_set_modes(math_mode, rng_mode, philox_key[0], philox_key[1])
+    if True in _libs:  # the tight build has its own copy of the process-wide modes
+        _libs[True].orc_set_modes(math_mode, rng_mode, philox_key[0], philox_key[1])
 
 
 # ---- known-answer helpers

@@ -39,6 +39,12 @@
 // Cost structure is kept faithful on purpose (528-byte by-value spectra,
 // per-ray heap vector + stable sort, per-sample get_rgb_early with CIE lerps,
 // double slab test for plain boxes) because this is also the timed CPU baseline.
+//
+// -DORACLE_TIGHT builds the same code with the four cost items SURVEY.md 8(d) lists removed -- spectra stored
+// 32 wide instead of 128, colour weights computed once per spectrum layout instead of per sample, closest hit
+// tracked without the heap vector + sort, per-ray reciprocals hoisted and the plain box's second slab test
+// reused -- and NOTHING else: every f32 operation and its order are unchanged, so the images are bit-identical
+// (tests/test_oracle_kat.py).  It is the "honest best-effort" CPU number reported beside the faithful one.
 
 #include <algorithm>
 #include <atomic>
@@ -134,6 +140,11 @@ constexpr float SPECULAR_MIN_RAY_DISTANCE = 0.0001f;          // shader.rs:14
 constexpr float PI_F = 3.14159265358979323846f;               // std::f32::consts::PI
 constexpr float FRAC_PI_2_F = 1.57079632679489661923f;
 constexpr int NBR_OF_SAMPLES_MAX = 128;                       // spectrum.rs:8
+#ifdef ORACLE_TIGHT
+constexpr int SPECTRUM_STORAGE = 32;  // tight build: spectra are stored as wide as the default sample count
+#else
+constexpr int SPECTRUM_STORAGE = NBR_OF_SAMPLES_MAX;
+#endif
 
 // ---------------------------------------------------------------- oracle modes
 // math_mode 0 ("native"): sin/cos/asin are the platform's f32 libm, which is what
@@ -160,7 +171,7 @@ inline float m_asin(float x) { return g_math_mode ? (float)std::asin((double)x) 
 // 128 floats no matter what nbr_of_samples is, exactly like the reference.
 struct Spectrum {
     size_t nbr_of_samples;
-    float intensities[NBR_OF_SAMPLES_MAX];
+    float intensities[SPECTRUM_STORAGE];
     float lo, hi;  // SpectrumType::EquidistantSamples(lo, hi)
 };
 
@@ -316,6 +327,7 @@ const M3 XYZ_TO_RGB_MATRIX = {{{2.041369f, -0.5649464f, -0.3446944f},   // spect
 // spectrum.rs:238-261.  The wavelength is ACCUMULATED in f32 (`wavelength +=
 // sample_distance` while `wavelength <= max`), so some sample counts generate
 // fewer than nbr_of_samples entries and the trailing intensities are ignored.
+#ifndef ORACLE_TIGHT
 V3 get_rgb_early(const Spectrum& s) {
     std::vector<V3> xyz_values;
     xyz_values.reserve(s.nbr_of_samples);
@@ -331,6 +343,30 @@ V3 get_rgb_early(const Spectrum& s) {
     for (const V3& v : xyz_values) fin = fin + v;
     return na::mul(XYZ_TO_RGB_MATRIX, fin);
 }
+#else
+// tight build: the per-sample list xyz(lambda_i) / n depends only on (n, lo, hi); it is built once per thread
+// with the very loop above and reused.  The products and the fold are the reference's, in the same order.
+V3 get_rgb_early(const Spectrum& s) {
+    thread_local std::vector<V3> weights;
+    thread_local size_t w_n = 0;
+    thread_local float w_lo = 0.0f, w_hi = 0.0f;
+    if (w_n != s.nbr_of_samples || w_lo != s.lo || w_hi != s.hi) {
+        weights.clear();
+        float sample_distance = (s.hi - s.lo) / (float)(s.nbr_of_samples - 1);
+        float wavelength = s.lo;
+        while (wavelength <= s.hi) {
+            weights.push_back(wavelength_to_XYZ(wavelength) / (float)s.nbr_of_samples);
+            wavelength += sample_distance;
+        }
+        w_n = s.nbr_of_samples;
+        w_lo = s.lo;
+        w_hi = s.hi;
+    }
+    V3 fin = {0.0f, 0.0f, 0.0f};
+    for (size_t i = 0; i < weights.size(); ++i) fin = fin + weights[i] * s.intensities[i];
+    return na::mul(XYZ_TO_RGB_MATRIX, fin);
+}
+#endif
 
 // ---------------------------------------------------------------- scene types
 struct Material {  // shader.rs:253-258
@@ -792,6 +828,7 @@ void miss_shader(Ray& ray, const RaytracingUniforms&) {  // shader.rs:460-463
 
 // shader.rs:468-495: linear scan with slab pre-test, keep t > 0, stable sort,
 // first(); closest beyond max_hit_distance => neither hit nor miss.
+#ifndef ORACLE_TIGHT
 void submit_ray(Ray& ray, const RaytracingUniforms& uniforms) {
     std::vector<std::pair<const Aabb*, float>> intersections;
     for (const Aabb& aabb : uniforms.aabbs) {
@@ -814,6 +851,58 @@ void submit_ray(Ray& ray, const RaytracingUniforms& uniforms) {
         miss_shader(ray, uniforms);
     }
 }
+#else
+// tight build: per-ray reciprocals hoisted (same values), the plain box reuses its bounds test instead of
+// repeating it (same numbers), and the closest hit is tracked instead of collected and sorted -- the first
+// strictly smaller t wins, which is what a stable sort + first() returns.
+static bool slab_inv(V3 o, const float inv[3], V3 pmin, V3 pmax, float& t_min_out, float& t_max_out) {
+    tl_counters.slab_tests++;
+    float t_min = -std::numeric_limits<float>::infinity();
+    float t_max = std::numeric_limits<float>::infinity();
+    for (int i = 0; i < 3; ++i) {
+        float t1 = (pmin[i] - o[i]) * inv[i];
+        float t2 = (pmax[i] - o[i]) * inv[i];
+        float t_near = t1, t_far = t2;
+        if (inv[i] < 0.0f) { t_near = t2; t_far = t1; }
+        t_min = rmax(t_min, t_near);
+        t_max = rmin(t_max, t_far);
+        if (t_max <= t_min) return false;
+    }
+    if (t_max < 0.0f) return false;
+    t_min_out = t_min;
+    t_max_out = t_max;
+    return true;
+}
+void submit_ray(Ray& ray, const RaytracingUniforms& uniforms) {
+    const float inv[3] = {1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z};
+    const Aabb* best = nullptr;
+    float best_t = 0.0f;
+    for (const Aabb& aabb : uniforms.aabbs) {
+        float b0, b1;
+        if (!slab_inv(ray.origin, inv, aabb.min, aabb.max, b0, b1)) continue;
+        std::optional<float> t;
+        if (aabb.aabb_type == AABBType::PlainBox) {
+            tl_counters.shape_plain++;
+            float mn = rmin(b0, b1);
+            t = mn >= 0.0f ? mn : rmax(b0, b1);
+        } else {
+            t = intersection_shader(ray, aabb);
+        }
+        if (t && *t > 0.0f && (!best || *t < best_t)) {
+            best = &aabb;
+            best_t = *t;
+        }
+    }
+    if (best) {
+        if (best_t <= ray.max_hit_distance) {
+            if (!ray.skip_hit_shader) hit_shader(ray, *best, best_t, uniforms);
+            else ray.hit = true;
+        }
+    } else {
+        miss_shader(ray, uniforms);
+    }
+}
+#endif
 
 // shader.rs:271-299 up to (not including) the colour conversion.
 Ray trace_primary(PixelPos pos, uint32_t w, uint32_t h, const RaytracingUniforms& uniforms) {
@@ -1055,7 +1144,7 @@ extern "C" {
 struct orc_scene { Scene s; };
 
 orc_scene* orc_scene_new(uint32_t n_lambda) {
-    if (n_lambda % 8 != 0 || n_lambda == 0 || n_lambda > NBR_OF_SAMPLES_MAX) return nullptr;  // spectrum.rs:37-38
+    if (n_lambda % 8 != 0 || n_lambda == 0 || n_lambda > SPECTRUM_STORAGE) return nullptr;  // spectrum.rs:37-38
     orc_scene* o = new orc_scene();
     o->s.n_lambda = n_lambda;
     o->s.lo = LO;
@@ -1477,6 +1566,13 @@ void orc_counters_get(uint64_t* out) {
                       c.shape_plain, c.shape_rotated, c.hits, c.self_hits, c.misses, c.lit, c.spec_hits, c.spec_dropped};
     std::memcpy(out, v, sizeof(v));
     std::memcpy(out + 14, c.depth_hist, sizeof(c.depth_hist));
+}
+int orc_is_tight() {
+#ifdef ORACLE_TIGHT
+    return 1;
+#else
+    return 0;
+#endif
 }
 unsigned orc_hardware_threads() { return std::max(1u, std::thread::hardware_concurrency()); }
 

@@ -174,3 +174,35 @@ def test_spectrum_radiance_and_normalize_restatement(oracle):
         n = O.spectrum_normalize(s)
         assert abs(float(O.get_rgb_early(n).max()) - 1.0) < 1e-5                     # spectrum.rs:364-368
         assert np.allclose(n / n[0], s / s[0], rtol=1e-5)                            # the shape is kept
+
+
+# --------------------------------------------------------------------------- the "tight" CPU build
+@pytest.mark.parametrize("name,arg", [("cornell", 0), ("default", 0), ("spheres", 30), ("prism", 0)])
+def test_tight_cpu_build_is_bit_identical_to_the_faithful_one(oracle, name, arg):
+    """liboracle_tight.so removes the reference's avoidable cost items (128-wide spectra, per-sample colour
+    weights, heap vector + sort per ray, double slab test) and nothing else: same images, same spectra, same
+    event counters, bit for bit."""
+    O = oracle
+    w, h, frames = 64, 48, 3
+    out = []
+    for tight in (False, True):
+        sc = O.Scene(32, name, arg, tight=tight)
+        img, spec = sc.render(w, h, frames, intended_frames=8, spectral=True, threads=2)
+        ids, t, _ = sc.primary(w, h, 0, 8)
+        out.append((img, spec, ids, t))
+    for a, b in zip(*out):
+        assert np.array_equal(a, b, equal_nan=True)
+    with pytest.raises(ValueError):
+        O.Scene(64, "cornell", tight=True)      # the tight build stores spectra 32 wide
+
+
+def test_tight_cpu_build_is_faster(oracle):
+    import time
+    O = oracle
+    dt = []
+    for tight in (False, True):
+        sc = O.Scene(32, "cornell", tight=tight)
+        t0 = time.perf_counter()
+        sc.render(160, 120, 2, intended_frames=8, threads=2)
+        dt.append(time.perf_counter() - t0)
+    assert dt[1] < dt[0]
