@@ -351,15 +351,20 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     n_launch = max(1, launches if args.integrator == 1 else stage_n[2])
     kernel_ms = (render_ms if args.integrator == 1 else stage_ms[2]) / n_launch
-    # Algorithmic HBM bytes, from THIS run's counters (rank 0).
-    #  * SURVEY.md 8(d), wavefront with HBM-resident path state: 576 B per path-bounce (ray 32 B + throughput 4*n_lambda +
-    #    radiance 4*n_lambda, read and written) + 4*n_lambda per accumulation write.  That is what the WAVEFRONT moves.
+    # Algorithmic HBM bytes of the dominant kernel, from THIS run's counters (rank 0).
+    #  * SURVEY.md 8(d)'s figure for a wavefront whose whole path state lives in HBM: 576 B per path-bounce (ray 32 B +
+    #    throughput 4*n_lambda + radiance 4*n_lambda, read and written) + 4*n_lambda per accumulation write (quoted beside).
+    #  * what THIS wavefront's k_shade moves: per path-bounce ray 32 B + hit 8 B read, throughput 4*n_lambda
+    #    read unless the path is fresh; ray 32 B + throughput 4*n_lambda written if the path goes on; radiance is not
+    #    carried per path -- a lit event adds 4*n_lambda to the pixel's record (read + write, the buffer exceeds L2).
     #  * the RESIDENT integrator keeps ray and throughput on chip; what it must move is the accumulation buffer, which
     #    is larger than L2 and whose every pixel record (4*n_lambda B) is read and written once per frame.
     bounces_rank0 = counters["rays_primary"] + counters["rays_continuation"]
     state_bytes = bounces_rank0 * 2 * (32 + 4 * N_LAMBDA + 4 * N_LAMBDA) + counters["lit"] * 4 * N_LAMBDA
+    shade_bytes = (bounces_rank0 * 40 + counters["rays_continuation"] * 4 * N_LAMBDA +
+                   counters["rays_continuation"] * (32 + 4 * N_LAMBDA) + counters["lit"] * 2 * 4 * N_LAMBDA)
     accum_bytes = counters["samples"] * 2 * 4 * N_LAMBDA
-    alg_bytes = accum_bytes if args.integrator == 1 else state_bytes
+    alg_bytes = accum_bytes if args.integrator == 1 else shade_bytes
     achieved_gbs = alg_bytes / n_launch / (kernel_ms * 1e-3) / 1e9
     traffic = None
     try:  # measured DRAM bytes of the dominant kernel (one ncu --set full capture, committed under profiles/)
@@ -379,7 +384,8 @@ def main():
                          "roofline_fp32 (north star: FP32 issue rate).  SURVEY 8(d)'s figure for an HBM-resident wavefront state "
                          "is given beside it: at this throughput it would need more than the HBM peak."
                          if args.integrator == 1 else
-                         "wavefront: SURVEY 8(d) HBM-resident path state, 576 B per path-bounce + 128 B per lit event")}
+                         "wavefront k_shade: ray + hit + throughput read, ray + throughput written for surviving paths, 256 B per lit "
+                         "event (accumulation record read + write); SURVEY 8(d)'s figure (radiance carried per path too) beside it")}
     sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
     fp32 = None
     if oc is not None:
