@@ -62,7 +62,7 @@ def main():
     srt.spectra_radiance(s)
     srt.spectra_normalize(s)
     assert srt.selftest_arith(1 << 16, 3) == 0
-    print(f"sanitize_cover: {len(done)} render configurations + tools ok")
+    print(f"cover_all_kernels: {len(done)} render configurations + tools ok")
 
 
 if __name__ == "__main__":
