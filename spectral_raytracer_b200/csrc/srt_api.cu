@@ -674,7 +674,12 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         sp.bvh_nodes = c->bvh_nodes;
         sp.bvh_prims = c->bvh_prims;
     } else {
-        for (uint32_t i = 0; i < n_objects; ++i) sp.obj[i] = dev_objs[i];
+        // index word of a linear-scan scene: (orig << 10) | (staged index << 2) | kind  (ClosestKey, srt_kernels.cuh)
+        static_assert(kMaxConstObjects <= 256, "staged index field of the index word");
+        for (uint32_t i = 0; i < n_objects; ++i) {
+            sp.obj[i] = dev_objs[i];
+            sp.obj[i].kind_orig = ((dev_objs[i].kind_orig >> 2) << 10) | (i << 2) | (dev_objs[i].kind_orig & 3u);
+        }
     }
 
     // lights

@@ -32,7 +32,7 @@ enum : uint32_t { kPlainBox = 0, kSphere = 1, kRotatedBox = 2 };
 // row-major Rotation3 (shader.rs:560-571); the inverse rotation is applied by transposed indexing.
 struct alignas(16) DevObject {
     float mn[3];
-    uint32_t kind_orig;  // (original index << 2) | kind
+    uint32_t kind_orig;  // (original index << 2) | kind; linear-scan scenes: (orig << 10) | (staged index << 2) | kind
     float mx[3];
     uint32_t material;
     float c[3];
