@@ -290,6 +290,7 @@ struct srt_ctx {
     DevObject* objects_g = nullptr;
     DevBvhNode* bvh_nodes = nullptr;
     uint32_t* bvh_prims = nullptr;
+    float4* frames = nullptr;  // SceneParams::frames
     uint64_t frames_accumulated = 0;
     uint64_t iterations = 0, launches = 0;
     float last_ms = 0.0f;
@@ -359,6 +360,7 @@ void free_ctx(srt_ctx* c) {
     cudaFree(c->objects_g);
     cudaFree(c->bvh_nodes);
     cudaFree(c->bvh_prims);
+    cudaFree(c->frames);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
     if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -714,6 +716,17 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         sp.mat_ext = c->mat_ext;
         sp.mat_refl = c->mat_refl;
         sp.tame = tame ? 1u : 0u;
+    }
+    // face_towards() frames of the box-face normals (cosine_direction), tabulated by the device code itself
+    {
+        sp.n_frame_rot = std::min(sp.n_rot, 4096u);
+        const uint32_t n_frames = 6u + 6u * sp.n_frame_rot;
+        CREATE_TRY(cudaMalloc(&c->frames, (size_t)n_frames * 3 * sizeof(float4)));
+        sp.frames = nullptr;
+        k_build_frames<<<(n_frames + kBlock - 1) / kBlock, kBlock>>>(sp, c->frames, n_frames, c->use_bvh ? 0 : 1);
+        CREATE_TRY(cudaGetLastError());
+        CREATE_TRY(cudaDeviceSynchronize());
+        sp.frames = c->frames;
     }
     // colour weights
     {

@@ -84,6 +84,10 @@ struct SceneParams {
     const DevObject* objects_g;
     const DevBvhNode* bvh_nodes;
     const uint32_t* bvh_prims;              // primitive slot -> object index
+    // face_towards() of every box-face normal (k_build_frames): 3 float4 per frame; frames 0..5 = the axis
+    // normals of plain boxes, 6 + 6*r + face = rotated box r (r < n_frame_rot)
+    const float4* frames;
+    uint32_t n_frame_rot, pad_frames;
     // lights
     float light_pos[kMaxLights][3];
     float light_e[kMaxLights][kMaxLambda];  // raw emission spectra
