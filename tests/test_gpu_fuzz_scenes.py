@@ -89,3 +89,48 @@ def test_random_scene_matches_oracle_sample_for_sample(oracle, seed):
                     tol = SAMPLE_RTOL * np.maximum(np.abs(wnt), max(np.nanmax(np.abs(wnt)), 1e-30) * 1e-6)
                     bad = (np.abs(got - wnt) > tol) & ~both_nan
                     assert bad.sum() == 0, (seed, integrator, accel, f, int(bad.sum()), bad.size)
+
+
+@pytest.mark.parametrize("order", ["plain-rot-plain", "rot-plain-plain", "plain-plain-rot", "sphere-first"])
+def test_ties_go_to_the_lowest_original_index(oracle, order):
+    """submit_ray sorts the candidates by t with a STABLE sort and takes the first (shader.rs:481-483): coincident
+    surfaces of different primitives -- two identical plain boxes, a rotated box with the identity rotation on top
+    of them, spheres inside each other touching a box face's plane -- must report the primitive that comes first in
+    the caller's list, whatever kind it is (the device scans the kinds in its own order).  Ids and distances bit-exact
+    against the oracle through both acceleration structures, per-sample spectra through both integrators."""
+    O = oracle
+    sc = O.Scene(32)
+    sc.set_camera((0.0, 0.25, -3.0), (0.0, -0.05, 1.0), (0.0, 1.0, 0.0), 50.0)
+    r = [sc.add_spectrum(np.full(32, v, np.float32)) for v in (0.2, 0.5, 0.9)]
+    e = sc.add_spectrum(np.full(32, 5.0, np.float32))
+    m = [sc.add_material(0.0, 0.0, s) for s in r]
+    c, l = (0.0, 0.0, 0.0), (1.0, 1.0, 1.0)
+    add = {"plain": lambda mat: sc.add_box(c, l, mat), "rot": lambda mat: sc.add_rotated_box(c, l, (0.0, 0.0, 0.0), mat),
+           "sphere": lambda mat: sc.add_sphere((0.0, 0.0, 0.0), 0.5, mat)}
+    kinds = {"plain-rot-plain": ("plain", "rot", "plain"), "rot-plain-plain": ("rot", "plain", "plain"),
+             "plain-plain-rot": ("plain", "plain", "rot"), "sphere-first": ("sphere", "sphere", "plain")}[order]
+    for k, mat in zip(kinds, m):
+        add[k](mat)
+    sc.add_box((0.0, -0.6, 0.0), (8.0, 0.2, 8.0), m[1])  # floor touching the boxes' bottom face (y = -0.5)
+    sc.add_light((1.5, 2.0, -2.0), e)
+    flat = flat_from_oracle(sc)
+    w, h, N = 96, 64, 4
+    O.set_modes(O.MATH_CANONICAL, O.RNG_PCG3D)
+    try:
+        want_ids, want_t, _ = sc.primary(w, h, frame=0, intended_frames=1)
+        want = sc.render(w, h, 1, first_frame=1, intended_frames=N, spectral=True, threads=4)[1]
+    finally:
+        O.set_modes(O.MATH_NATIVE, O.RNG_PCG3D)
+    assert len(np.unique(want_ids[want_ids >= 0])) >= 2  # the coincident stack and the floor are both in view
+    for accel in (srt.ACCEL_LINEAR, srt.ACCEL_BVH):
+        with srt.Renderer(flat, w, h, intended_frames=1, math=srt.MATH_EXACT, accel=accel) as rr:
+            ids, t = rr.primary_ids(0)
+        assert np.array_equal(ids, want_ids), (order, accel, int((ids != want_ids).sum()))
+        assert np.array_equal(t, want_t, equal_nan=True)
+        for integrator in (srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT):
+            with srt.Renderer(flat, w, h, intended_frames=N, math=srt.MATH_EXACT, accel=accel, integrator=integrator) as rr:
+                got = _one_frame(rr, 1)
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            tol = SAMPLE_RTOL * np.maximum(np.abs(want), max(np.nanmax(np.abs(want)), 1e-30) * 1e-6)
+            bad = (np.abs(got - want) > tol) & ~(np.isnan(got) & np.isnan(want))
+            assert bad.sum() == 0, (order, accel, integrator, int(bad.sum()))
