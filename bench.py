@@ -11,17 +11,24 @@ for every pixel = 132.7 M samples; the default K=16 steps are exactly the 1024 s
 With N GPUs every rank renders its own --frames-per-step frames per step (frame-sharded, weak scaling), and
 the spectral accumulation buffers are summed onto rank 0 with one NCCL reduce inside the timed region.
 
-Prints ONE JSON line on rank 0 (see the keys at the bottom of main()).
+Prints ONE JSON line on rank 0.  Beside the contract's keys it carries, measured in the same run:
+  roofline       FP32-issue roofline of the dominant kernel (the bound SURVEY.md 8d names); roofline_hbm beside it
+  exact_math / philox   the same workload in the sample-exact math mode / with the north star's Philox RNG
+  configs        BASELINE.json's other configs (C0, C2, C3, C4), each rank rendering its shard, reduce included
+  strong         the named config as a fixed job: 1024 spp split over the N ranks, reduce + resolve inside the clock
+  reduce_check   (N >= 2) srt_reduce of libsrt_nccl.so against the torch.distributed path, and its time
+  rmse           the converged-image gate: 480x270, 1024 spp, production math vs the committed oracle image
 """
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
+import re
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -42,6 +49,7 @@ def emit(line: dict) -> None:
 
 WIDTH, HEIGHT, N_LAMBDA, BOUNCES = 1920, 1080, 32, 30
 SCENE = "cornell"
+SPP_NAMED = 1024  # BASELINE.json config[1]
 
 # SURVEY.md 8(d) cost table: f32 lane-operations per event
 COST = dict(slab=28, shape_sphere=46, shape_plain=31, shape_rotated=70, raygen=75, hit_common=36 + 24,
@@ -49,7 +57,7 @@ COST = dict(slab=28, shape_sphere=46, shape_plain=31, shape_rotated=70, raygen=7
             resolve=15 + 8)
 
 
-def ops_per_sample(c: dict, n_lambda: int, n_lights: int) -> float:
+def ops_per_sample(c: dict, n_lambda: int) -> float:
     """Algorithmic f32 operations per sample from the ORACLE's event counters."""
     s = c["samples"]
     shapes = c["shape_sphere"] + c["shape_plain"] + c["shape_rotated"]
@@ -108,7 +116,8 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_run(n_frames: int, threads: int, first_frame: int = 0, counters: bool = False, tight: bool = False):
+def cpu_reference_run(n_frames: int, threads: int, first_frame: int = 0, counters: bool = False, tight: bool = False,
+                      width: int = WIDTH, height: int = HEIGHT):
     """The reference's CPU path (oracle/oracle.cpp, platform libm, row-per-task pool) on n_frames of the
     bench workload.  Returns (seconds, samples, counters|None, image).  The oracle is only ever the baseline / the
     checker here."""
@@ -119,10 +128,19 @@ def cpu_reference_run(n_frames: int, threads: int, first_frame: int = 0, counter
     if counters:
         O.counters_reset()
     t0 = time.perf_counter()
-    img = sc.render(WIDTH, HEIGHT, n_frames, first_frame=first_frame, intended_frames=1024, max_bounces=BOUNCES,
+    img = sc.render(width, height, n_frames, first_frame=first_frame, intended_frames=SPP_NAMED, max_bounces=BOUNCES,
                     threads=threads)
     dt = time.perf_counter() - t0
-    return dt, n_frames * WIDTH * HEIGHT, (O.counters() if counters else None), img
+    return dt, n_frames * width * height, (O.counters() if counters else None), img
+
+
+def workload_config() -> dict:
+    """What is measured -- the same dictionary in both arms (what differs between them is in `arm`)."""
+    return {"workload": f"Cornell box (main.rs:1538-1635) {WIDTH}x{HEIGHT}, {N_LAMBDA} spectral samples, {BOUNCES} bounces, "
+                        f"{SPP_NAMED} spp (BASELINE.json config 1)",
+            "scene": SCENE, "width": WIDTH, "height": HEIGHT, "n_lambda": N_LAMBDA, "max_bounces": BOUNCES,
+            "spp": SPP_NAMED, "rng": "pcg3d_reference",
+            "cache": "working set (265 MB spectral accumulation buffer per GPU) exceeds the 126 MB L2; no explicit flush"}
 
 
 def run_reference(args, rank: int, world: int):
@@ -145,7 +163,9 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": "samples/s at 1080p Cornell box", "value": value, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, reference=True),
+        "config": workload_config(),
+        "arm": {"frames_per_step": 1, "integrator": "cpu", "math": "platform libm (glibc)",
+                "parallelism": f"{threads} host threads, one task per image row (main.rs:1286-1307)"},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} steps x 1 frame of the 1920x1080 Cornell box (2.07 M samples each), "
                                    "C++ restatement of the Rust reference (no Rust toolchain in this image)"},
@@ -155,16 +175,32 @@ def run_reference(args, rank: int, world: int):
     emit(line)
 
 
-def workload_config(args, world: int, reference: bool = False) -> dict:
-    return {"workload": f"Cornell box (main.rs:1538-1635) {WIDTH}x{HEIGHT}, {N_LAMBDA} spectral samples, "
-                        f"{BOUNCES} bounces; 1 step = {1 if reference else args.frames_per_step} frame(s) per rank",
-            "scene": SCENE, "width": WIDTH, "height": HEIGHT, "n_lambda": N_LAMBDA, "max_bounces": BOUNCES,
-            "frames_per_step": 1 if reference else args.frames_per_step,
-            "spp_total": (1 if reference else args.frames_per_step) * args.steps * world,
-            "integrator": "cpu" if reference else ("resident" if args.integrator == 1 else "wavefront"),
-            "rng": "pcg3d_reference" if args.rng == 0 else "philox", "math": "fast" if args.math == 0 else "exact",
-            "parallelism": f"frames sharded over {world} GPU(s), NCCL reduce of spectral accumulation buffers",
-            "cache": "working set (265 MB accumulation buffer per GPU) exceeds the 126 MB L2; no explicit flush"}
+def newest_ncu_traffic(kernel: str):
+    """DRAM bytes per sample of `kernel` from the NEWEST profiles/rNN_<kernel>_vMM_ncu_summary.txt (one ncu --set full
+    capture per kernel change, scripts/ncu_summary.py --samples N writes the sample count of the captured launch)."""
+    best = None
+    for path in glob.glob(os.path.join(ROOT, "profiles", f"r*_{kernel}_*ncu_summary.txt")):
+        m = re.search(r"r(\d+)_" + re.escape(kernel) + r"_v(\d+)", os.path.basename(path))
+        if not m:
+            continue
+        key = (int(m.group(1)), int(m.group(2)))
+        if best is None or key > best[0]:
+            best = (key, path)
+    if best is None:
+        return None, None
+    rd = wr = samples = None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for line in open(best[1]):
+        f = line.split()
+        if len(f) >= 3 and f[0] == "dram__bytes_read.sum" and f[2] in unit:
+            rd = float(f[1]) * unit[f[2]]
+        elif len(f) >= 3 and f[0] == "dram__bytes_write.sum" and f[2] in unit:
+            wr = float(f[1]) * unit[f[2]]
+        elif len(f) >= 2 and f[0] == "samples_in_launch":
+            samples = float(f[1])
+    if rd is None or wr is None or not samples:
+        return None, os.path.relpath(best[1], ROOT)
+    return (rd + wr) / samples, os.path.relpath(best[1], ROOT)
 
 
 def main():
@@ -178,6 +214,7 @@ def main():
     ap.add_argument("--rng", type=int, default=0, help="0 pcg3d (reference), 1 philox")
     ap.add_argument("--math", type=int, default=0, help="0 fast (CUDA f32 libm), 1 exact")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline numbers only (skip configs / strong / modes)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3  # timing rule: W >= 3
@@ -195,7 +232,7 @@ def main():
 
     import spectral_raytracer_b200 as srt
     from spectral_raytracer_b200 import scenes
-    from spectral_raytracer_b200.distributed import accum_as_tensor, reduce_sum_
+    from spectral_raytracer_b200.distributed import accum_as_tensor, frame_shard, reduce_contexts_
 
     if not torch.cuda.is_available() or srt.native.lib().srt_device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device -- the render backend has no CPU fallback")
@@ -207,21 +244,66 @@ def main():
     F, K, W = args.frames_per_step, args.steps, args.warmup
     npix = WIDTH * HEIGHT
     total_frames = (K + W) * F * world
-    flat = scenes.preset(SCENE, N_LAMBDA)
-    r = srt.Renderer(flat, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=max(1024, total_frames), rng=args.rng,
-                     math=args.math, integrator=args.integrator, device=local_rank)
-    r.set_profiling(args.integrator == 0)
-    acc_t = accum_as_tensor(r)
-    host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
-    host_np = host_img.numpy()
-
-    def frame_base(step):  # rank-th block of F frames of global step `step`
-        return (step * world + rank) * F
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(xs):
+        t = torch.tensor(list(xs), dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t)
+        return [float(v) for v in t]
+
+    def timed_render(r, n_steps, n_warm, frames, *, reduce=True):
+        """n_warm untimed + n_steps timed steps of `frames` frames on every rank (each rank its own frame ids), device
+        time from the context's CUDA events; with N > 1 one reduce of the accumulation buffers onto rank 0 inside the
+        clock.  Returns whole-job numbers (times: max over ranks)."""
+        acc = accum_as_tensor(r)
+        base = lambda s: (s * world + rank) * frames  # noqa: E731
+        for s in range(n_warm):
+            r.render_frames(base(s), frames)
+        if world > 1 and reduce:
+            dist.reduce(acc.clone(), dst=0)  # warm NCCL for this message size
+        r.clear()
+        r.reset_counters()
+        barrier()
+        ms, launches = 0.0, 0
+        for s in range(n_steps):
+            r.render_frames(base(n_warm + s), frames)
+            m, n = r.last_render_stats()
+            ms += m
+            launches += n
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        if world > 1 and reduce:
+            dist.reduce(acc, dst=0)
+            if rank == 0:
+                r.frames_accumulated = n_steps * frames * world
+        ev1.record()
+        barrier()
+        reduce_ms = ev0.elapsed_time(ev1) if world > 1 and reduce else 0.0
+        total_ms = max_over_ranks(ms + reduce_ms)
+        c = r.counters()
+        samples, prim, cont, shad = sum_over_ranks([c["samples"], c["rays_primary"], c["rays_continuation"], c["rays_shadow"]])
+        return {"samples": samples, "rays": prim + cont + shad, "ms": total_ms, "render_ms_rank": ms, "reduce_ms": reduce_ms,
+                "launches": launches, "counters_rank": c}
+
+    flat = scenes.preset(SCENE, N_LAMBDA)
+    r = srt.Renderer(flat, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=max(SPP_NAMED, total_frames), rng=args.rng,
+                     math=args.math, integrator=args.integrator, device=local_rank)
+    r.set_profiling(args.integrator == 0)
+    acc_t = accum_as_tensor(r)
+
+    def frame_base(step):  # rank-th block of F frames of global step `step`
+        return (step * world + rank) * F
 
     # ---------------- device-resident throughput (`value`)
     for s in range(W):
@@ -253,73 +335,177 @@ def main():
     reduce_ms = ev0.elapsed_time(ev1)
     wall = time.perf_counter() - wall0
     clk = clocks.stop()
-    t_rank = torch.tensor([render_ms + reduce_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_rank, op=dist.ReduceOp.MAX)
-    total_ms = float(t_rank.item())
+    total_ms = max_over_ranks(render_ms + reduce_ms)
     counters = r.counters()
-    csum = torch.tensor([counters[k] for k in ("samples", "rays_primary", "rays_continuation", "rays_shadow", "lit")],
-                        dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(csum)
-    samples, rays = float(csum[0]), float(csum[1] + csum[2] + csum[3])
+    samples, prim, cont, shad, lit = sum_over_ranks([counters[k] for k in ("samples", "rays_primary", "rays_continuation",
+                                                                            "rays_shadow", "lit")])
+    rays = prim + cont + shad
     assert samples == K * F * npix * world, (samples, K * F * npix * world)
     value = samples / (total_ms * 1e-3)
 
     # ---------------- end to end through the C ABI with host buffers (`e2e`)
-    # per step: render F frames, resolve spectrum -> RGB on the device and read the RGBA f32 image back
-    # into pinned host memory (what App::render does every frame with FrameUpdate, main.rs:1343-1348);
-    # host -> device per step = the kernel-parameter block (scene) of every launch + the control block.
+    # App::render's protocol (main.rs:1338-1357) through srt_render_progressive: per step F frames, then the RGBA8
+    # image of everything accumulated so far (AppActions::FrameUpdate: From<CustomImage> for DynamicImage) is resolved
+    # on the device and copied into pinned host memory on a second stream while the next step renders, and handed to
+    # the host callback; at the end the f32 image (CustomImage.data) is read back as well.  host -> device per step =
+    # the kernel-parameter block (scene) of every launch + the control block.
     r.clear()
+    host_img = torch.empty((HEIGHT, WIDTH, 4), dtype=torch.float32).pin_memory()
+    host_np = host_img.numpy()
+    seen = []
+    checksum = [0]
+
+    def on_update(done, total, img):
+        seen.append(done)
+        checksum[0] += int(img[::97, ::89, :3].sum())  # the host really reads the delivered image
+        return False
+
+    r.render_progressive(0, 1, 1, lambda *a: False, preview=True)  # (allocates the preview buffers / second stream: untimed)
+    r.clear()
+    seen.clear()
     barrier()
+    l0 = r.counters()["kernel_launches"]
     e0 = time.perf_counter()
-    e2e_launches = 0
-    for s in range(K):
-        r.render_frames(frame_base(W + s), F)
-        e2e_launches += r.last_render_stats()[1] + 1
+    r.render_progressive((W * world + rank * K) * F, K * F, F, on_update, preview=True)  # (frame ids disjoint across ranks)
+    if world > 1:
+        reduce_contexts_(r, dst=0)
+    if rank == 0:
         r.resolve_rgba_f32(host_np)
-    if world > 1:
-        total = reduce_sum_(acc_t, K * F, dst=0)
-        if rank == 0:
-            r.frames_accumulated = total
-            r.resolve_rgba_f32(host_np)
     barrier()
-    e_rank = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e_rank, op=dist.ReduceOp.MAX)
-    e2e_value = samples / float(e_rank.item())
+    e2e_s = max_over_ranks(time.perf_counter() - e0)
+    assert len(seen) == K and seen[-1] == K * F
+    e2e_value = samples / e2e_s
+    e2e_launches = r.counters()["kernel_launches"] - l0
     scene_param_bytes = int(srt.native.lib().srt_launch_param_bytes())  # sizeof(SceneParams), passed by value with every launch
     h2d = int(e2e_launches / K * scene_param_bytes + 32)
-    d2h = int(host_np.nbytes + 32 * max(1, e2e_launches // (3 * K)))
+    d2h = int(WIDTH * HEIGHT * 4 + host_np.nbytes / K)
 
-    # ---------------- CPU baseline (rank 0, N=1): bounded sample of the same workload
-    cpu = None
-    cpu_tight = None
-    oc = None
-    rmse = None
+    extras = {}
+    if not args.no_extras:
+        # ---------------- the same workload in the other modes (device-timed, 4 steps each)
+        for key, kw in (("exact_math", dict(math=1, rng=0)), ("philox", dict(math=0, rng=1))):
+            with srt.Renderer(flat, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=SPP_NAMED, integrator=args.integrator,
+                              device=local_rank, **kw) as rr:
+                t = timed_render(rr, 4, 1, F, reduce=False)
+                extras[key] = {"value": t["samples"] / (t["ms"] * 1e-3), "unit": "samples/s", "steps": 4, "frames_per_step": F,
+                               "what": ("SRT_MATH_EXACT: correctly rounded sin / cos / asin, the reference's operation order in the light "
+                                        "term -- the mode whose samples equal the oracle's one by one" if key == "exact_math" else
+                                        "SRT_RNG_PHILOX: Philox4x32-10 keyed (pixel, frame, bounce), the north star's RNG")}
+
+        # ---------------- BASELINE.json's other configs, every rank its shard of frames, reduce inside the clock
+        cfgs = [("C0", "default scene 400x300, 64 iterations (the reference workload)", "default", 0, 400, 300, 64, 64, 4),
+                ("C2", "prism dispersion (extension) 1920x1080, 4096 spp", "prism", 0, 1920, 1080, 4096, 32, 3),
+                ("C3", "Cornell box 3840x2160, 16384 spp", "cornell", 0, 3840, 2160, 16384, 8, 3),
+                ("C4", "10 000 random spheres (BVH) 1920x1080, 1024 spp", "spheres", 10000, 1920, 1080, 1024, 16, 3)]
+        extras["configs"] = {}
+        for cid, desc, preset, arg, w, h, spp, frames, steps in cfgs:
+            fl = scenes.preset(preset, N_LAMBDA, arg)
+            with srt.Renderer(fl, w, h, max_bounces=BOUNCES, intended_frames=spp, device=local_rank) as rr:
+                t = timed_render(rr, steps, 1, frames)
+                sps = t["samples"] / (t["ms"] * 1e-3)
+                extras["configs"][cid] = {"config": desc, "samples_per_s": sps, "mrays_per_s": t["rays"] / (t["ms"] * 1e-3) / 1e6,
+                                          "frames_per_rank_and_step": frames, "steps": steps, "ms": t["ms"], "reduce_ms": t["reduce_ms"],
+                                          "reduce_mbytes": w * h * N_LAMBDA * 4 / 1e6 if world > 1 else 0.0,
+                                          "projected_seconds_for_config": spp * w * h / sps}
+
+        # ---------------- the named config as a FIXED job: 1024 spp split over the ranks, reduce + resolve in the clock
+        with srt.Renderer(flat, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=SPP_NAMED, integrator=args.integrator,
+                          device=local_rank) as rr:
+            rr.render_frames(SPP_NAMED, 8)  # warm
+            rr.clear()
+            first, count = frame_shard(0, SPP_NAMED, rank, world)
+            barrier()
+            t0 = time.perf_counter()
+            done = 0
+            dev_ms = 0.0
+            while done < count:
+                n = min(F, count - done)
+                rr.render_frames(first + done, n)
+                dev_ms += rr.last_render_stats()[0]
+                done += n
+            if world > 1:
+                reduce_contexts_(rr, dst=0)
+            if rank == 0:
+                assert rr.frames_accumulated == SPP_NAMED
+                rr.resolve_rgba_f32(host_np)
+            barrier()
+            strong_s = max_over_ranks(time.perf_counter() - t0)
+            extras["strong"] = {"what": f"{SPP_NAMED} spp of the 1080p Cornell box split over {world} rank(s): render in launches of <= {F} "
+                                        "frames, NCCL reduce onto rank 0, resolve + read-back of the f32 image there; wall clock between "
+                                        "barriers, max over ranks",
+                                "seconds": strong_s, "value": SPP_NAMED * npix / strong_s, "unit": "samples/s",
+                                "render_ms_max": max_over_ranks(dev_ms), "frames_per_rank": count}
+
+        # ---------------- srt_reduce (libsrt_nccl.so: one process, one context per device) against the torch path
+        if world > 1:
+            barrier()
+            if rank == 0:
+                try:
+                    from spectral_raytracer_b200 import reduce_contexts
+                    w2, h2, n2 = 480, 270, 8
+                    with srt.Renderer(flat, w2, h2, intended_frames=n2, device=0) as whole:
+                        whole.render_frames(0, n2)
+                        want = whole.resolve_rgba_f32()
+                    ctxs = [srt.Renderer(flat, w2, h2, intended_frames=n2, device=d) for d in range(world)]
+                    for d, c in enumerate(ctxs):
+                        f0, cnt = frame_shard(0, n2, d, world)
+                        if cnt:
+                            c.render_frames(f0, cnt)
+                    reduce_contexts(ctxs)
+                    got = ctxs[0].resolve_rgba_f32()
+                    ok = bool(ctxs[0].frames_accumulated == n2 and np.allclose(got, want, rtol=1e-5, atol=1e-6) and
+                              all(c.frames_accumulated == 0 for c in ctxs[1:]))
+                    for c in ctxs:
+                        c.close()
+                    # the time of the real message sizes (communicators are cached after the first call)
+                    times = {}
+                    for label, (w3, h3) in (("1080p_265MB", (1920, 1080)), ("4k_1062MB", (3840, 2160))):
+                        ctxs = [srt.Renderer(flat, w3, h3, intended_frames=4, device=d) for d in range(world)]
+                        for c in ctxs:
+                            c.render_frames(0, 1)
+                        reduce_contexts(ctxs)  # creates the communicators
+                        best = 1e30
+                        for _ in range(3):
+                            best = min(best, reduce_contexts(ctxs))
+                        times[label] = best
+                        for c in ctxs:
+                            c.close()
+                    extras["reduce_check"] = {"ok": ok, "max_abs_diff": float(np.abs(got - want).max()), "devices": world,
+                                              "srt_reduce_ms": times,
+                                              "what": "srt_reduce (libsrt_nccl.so, single process, one context per device, cached communicators) "
+                                                      "vs one context rendering all frames; then device time of reducing full-size buffers"}
+                except Exception as e:  # never lose the headline line over the extra check
+                    extras["reduce_check"] = {"ok": False, "error": repr(e)}
+            barrier()
+
+    # ---------------- converged-image gate + CPU baseline (rank 0)
+    cpu = cpu_tight = oc = rmse = None
+    if rank == 0:
+        gpath = os.path.join(ROOT, "tests", "golden", "converged_cornell_480x270_1024spp.npz")
+        if os.path.exists(gpath) and not args.no_extras:
+            g = np.load(gpath)
+            gw, gh, gspp = int(g["width"]), int(g["height"]), int(g["spp"])
+            goc = dict(zip([str(k) for k in g["counter_names"]], [int(v) for v in g["counter_values"]]))
+            with srt.Renderer(flat, gw, gh, intended_frames=gspp, max_bounces=BOUNCES, integrator=args.integrator, rng=args.rng,
+                              math=args.math, device=local_rank) as rr:
+                rr.render_frames(0, gspp)
+                got = rr.resolve_rgba_f32()[..., :3].astype(np.float64)
+                gc = rr.counters()
+            want = g["rgb"].astype(np.float64)
+            rmse = {"rel_rmse_vs_cpu": float(np.sqrt(np.mean((got - want) ** 2)) / want.mean()),
+                    "mean_ratio": float(got.mean() / want.mean()),
+                    "self_hit_rate": gc["self_hits"] / gc["hits"], "cpu_self_hit_rate": goc["self_hits"] / goc["hits"],
+                    "thresholds": {"rel_rmse": 0.03, "mean_ratio": 0.002, "self_hit_rate_rel": 0.01},
+                    "what": f"Cornell box {gw}x{gh}, {gspp} spp: this run's GPU image (the bench's math / rng mode) against the committed "
+                            "image of the CPU reference port with the same pcg3d keys (tests/golden/make_converged_cornell.py); relative RMSE "
+                            "of linear RGB, ratio of the means, rate of rounding-level self-intersections (tests/test_gpu_scale_parity.py "
+                            "asserts the same thresholds)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle as O
         threads = O.hardware_threads()
         dt, n, oc, _ = cpu_reference_run(1, threads, counters=True)
         frames = int(min(24, max(1, 12.0 / dt)))
-        dt2, n2, _, cpu_img = cpu_reference_run(frames, threads, first_frame=1)
-        # (the reference blends frame f with ratio 1 / (f + 1), custom_image.rs:71-76: started at frame 1 on an empty image the
-        # running mean counts an all-zero frame 0 -- undo that to get the mean of the frames actually rendered)
-        cpu_img = cpu_img * np.float32((frames + 1) / frames)
-        # RMSE vs the CPU reference (BASELINE.json's metric): the same frames on the GPU, production settings, against
-        # the image the CPU baseline just rendered; relative RMSE on linear f32 RGB (SURVEY 8d gate 3).  The noise floor
-        # beside it is the same statistic for DISJOINT frames (what two independent estimates of this length differ by).
-        def rel_rmse(a, b):
-            ok = np.isfinite(a).all(axis=2) & np.isfinite(b).all(axis=2)
-            a, b = a[ok].astype(np.float64), b[ok].astype(np.float64)
-            return float(np.sqrt(np.mean((a - b) ** 2)) / np.mean(b))
-        with srt.Renderer(flat, WIDTH, HEIGHT, intended_frames=1024, max_bounces=BOUNCES, integrator=args.integrator,
-                          device=local_rank) as rr:
-            rr.render_frames(1, frames)
-            same = rr.resolve_rgba_f32()[..., :3]
-            rr.clear()
-            rr.render_frames(1 + frames, frames)
-            other = rr.resolve_rgba_f32()[..., :3]
+        dt2, n2, _, _ = cpu_reference_run(frames, threads, first_frame=1)
         # the same port without the reference's avoidable cost items (oracle.cpp -DORACLE_TIGHT, bit-identical images)
         frames_t = max(1, frames // 2)
         dt3, n3, _, _ = cpu_reference_run(frames_t, threads, first_frame=1, tight=True)
@@ -327,16 +513,16 @@ def main():
                      "sample": f"{frames_t} frames ({n3 / 1e6:.1f} M samples, {dt3:.1f} s) of the same workload with the tight build of "
                                "the port: spectra stored 32 wide, colour weights computed once, closest hit tracked without heap "
                                "vector + sort, reciprocals hoisted -- same arithmetic, bit-identical images"}
-        rmse = {"rel_rmse_vs_cpu": rel_rmse(same, cpu_img[..., :3]), "noise_floor": rel_rmse(other, cpu_img[..., :3]),
-                "mean_ratio": float(np.nanmean(same) / np.nanmean(cpu_img[..., :3])), "frames": frames,
-                "what": "1920x1080 Cornell box, the same frame ids on the GPU (production math) and on the CPU reference port; "
-                        "relative RMSE of linear RGB; noise_floor = disjoint frame ids"}
         cpu = {"value": (n + n2) / (dt + dt2), "unit": "samples/s", "cores": threads, "kind": "port",
                "sample": f"{frames + 1} frames of the same 1920x1080 Cornell box ({(n + n2) / 1e6:.1f} M samples, "
                          f"{dt + dt2:.1f} s), C++ restatement of the Rust reference with its cost structure "
                          "(row-per-task pool, 528-byte spectra, per-ray Vec + sort, per-sample get_rgb_early)"}
+    elif rank == 0:
+        # event counters for the algorithmic op count only: one small frame of the same scene on the CPU port
+        _, _, oc, _ = cpu_reference_run(1, 0, counters=True, width=480, height=270)
 
     if rank != 0:
+        r.close()
         if world > 1:
             dist.destroy_process_group()
         return
@@ -347,18 +533,33 @@ def main():
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    kernel = "k_resident" if args.integrator == 1 else "k_shade"
     n_launch = max(1, launches if args.integrator == 1 else stage_n[2])
     kernel_ms = (render_ms if args.integrator == 1 else stage_ms[2]) / n_launch
-    # Algorithmic HBM bytes of the dominant kernel, from THIS run's counters (rank 0).
-    #  * SURVEY.md 8(d)'s figure for a wavefront whose whole path state lives in HBM: 576 B per path-bounce (ray 32 B +
-    #    throughput 4*n_lambda + radiance 4*n_lambda, read and written) + 4*n_lambda per accumulation write (quoted beside).
-    #  * what THIS wavefront's k_shade moves: per path-bounce ray 32 B + hit 8 B read, throughput 4*n_lambda
-    #    read unless the path is fresh; ray 32 B + throughput 4*n_lambda written if the path goes on; radiance is not
-    #    carried per path -- a lit event adds 4*n_lambda to the pixel's record (read + write, the buffer exceeds L2).
-    #  * the RESIDENT integrator keeps ray and throughput on chip; what it must move is the accumulation buffer, which
-    #    is larger than L2 and whose every pixel record (4*n_lambda B) is read and written once per frame.
+    samples_per_launch = counters["samples"] / n_launch
+    # (1) FP32 issue -- the bound SURVEY.md 8(d) names: algorithmic lane-ops per sample = oracle event counters x cost table
+    sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    ops = ops_per_sample(oc, N_LAMBDA)
+    peak_ops = 148 * 128 * sm_mhz * 1e6
+    kernel_sps = samples_per_launch / (kernel_ms * 1e-3)  # rank 0's kernel alone
+    traffic_per_sample, traffic_src = newest_ncu_traffic(kernel)
+    roofline = {"bound": "fp32_issue", "kernel": kernel, "achieved": kernel_sps * ops / 1e12, "peak": peak_ops / 1e12, "unit": "Tlane-op/s",
+                "frac": kernel_sps * ops / peak_ops,
+                "traffic": traffic_per_sample * samples_per_launch if traffic_per_sample else None,
+                "traffic_source": traffic_src, "traffic_what": "measured DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of "
+                                                               "the newest ncu --set full summary under profiles/, scaled to this launch's samples)",
+                "ops_per_sample": ops, "kernel_ms_per_launch": kernel_ms, "samples_per_launch": samples_per_launch,
+                "peak_source": f"148 SMs x 128 lanes x SM clock observed during the run ({sm_mhz:.0f} MHz)",
+                "note": "SURVEY 8(d) cost table x the CPU port's event counters on the same scene (1 op = one f32 add / mul / min / max / "
+                        "compare / select; div, sqrt, rcp and libm calls count 1); achieved = samples/s of the kernel on rank 0, timed with "
+                        "CUDA events on its own stream, x ops per sample"}
+    # (2) HBM, beside it.  Algorithmic bytes of the dominant kernel from THIS run's counters (rank 0):
+    #  * resident integrator: ray and throughput stay on chip; what it must move is the accumulation buffer, larger than L2 --
+    #    every pixel record (4*n_lambda B) is read and written once per frame;
+    #  * wavefront k_shade: per path-bounce ray 32 B + hit 8 B read, throughput 4*n_lambda read unless fresh; ray +
+    #    throughput written if the path goes on; a lit event adds 4*n_lambda to the pixel's record (read + write);
+    #  * SURVEY.md 8(d)'s figure for a wavefront whose whole path state lives in HBM is quoted beside it.
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     bounces_rank0 = counters["rays_primary"] + counters["rays_continuation"]
     state_bytes = bounces_rank0 * 2 * (32 + 4 * N_LAMBDA + 4 * N_LAMBDA) + counters["lit"] * 4 * N_LAMBDA
     shade_bytes = (bounces_rank0 * 40 + counters["rays_continuation"] * 4 * N_LAMBDA +
@@ -366,54 +567,39 @@ def main():
     accum_bytes = counters["samples"] * 2 * 4 * N_LAMBDA
     alg_bytes = accum_bytes if args.integrator == 1 else shade_bytes
     achieved_gbs = alg_bytes / n_launch / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:  # measured DRAM bytes of the dominant kernel (one ncu --set full capture, committed under profiles/)
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        key = "k_resident" if args.integrator == 1 else "k_shade"
-        if key in tr:
-            traffic = tr[key]["dram_bytes_per_sample"] * counters["samples"] / n_launch
-    except OSError:
-        pass
-    roofline = {"bound": "hbm", "kernel": "k_resident" if args.integrator == 1 else "k_shade",
-                "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / n_launch, "peak_source": peak_src,
-                "algorithmic_bytes_per_sample": alg_bytes / max(1, counters["samples"]),
-                "survey_8d_hbm_resident_state_bytes_per_sample": state_bytes / max(1, counters["samples"]),
-                "note": ("resident integrator: path state stays on chip, the algorithmic HBM traffic is the accumulation buffer "
-                         "(one 128-byte pixel record read + written per sample); the kernel is bound by instruction issue, see "
-                         "roofline_fp32 (north star: FP32 issue rate).  SURVEY 8(d)'s figure for an HBM-resident wavefront state "
-                         "is given beside it: at this throughput it would need more than the HBM peak."
-                         if args.integrator == 1 else
-                         "wavefront k_shade: ray + hit + throughput read, ray + throughput written for surviving paths, 256 B per lit "
-                         "event (accumulation record read + write); SURVEY 8(d)'s figure (radiance carried per path too) beside it")}
-    sm_mhz = clk.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
-    fp32 = None
-    if oc is not None:
-        ops = ops_per_sample(oc, N_LAMBDA, 1)
-        peak_ops = 148 * 128 * sm_mhz * 1e6
-        fp32 = {"bound": "fp32_issue", "ops_per_sample": ops, "achieved": value * ops / 1e12,
-                "peak": peak_ops / 1e12, "unit": "Tlane-op/s", "frac": value * ops / peak_ops,
-                "note": "SURVEY 8(d) cost table x oracle event counters on the same config; peak = 148 SMs x 128 lanes "
-                        "x SM clock observed during the run"}
+    roofline_hbm = {"bound": "hbm", "kernel": kernel, "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                    "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_sample": alg_bytes / max(1, counters["samples"]),
+                    "measured_dram_bytes_per_sample": traffic_per_sample,
+                    "survey_8d_hbm_resident_state_bytes_per_sample": state_bytes / max(1, counters["samples"]),
+                    "note": "not the binding roofline: the resident integrator keeps the path state on chip" if args.integrator == 1 else
+                            "wavefront k_shade: ray + hit + throughput read, ray + throughput written for surviving paths, 256 B per lit event"}
 
     line = {
         "metric": "samples/s at 1080p Cornell box", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": workload_config(),
+        "arm": {"frames_per_step": F, "spp_total": F * K * world, "integrator": "resident" if args.integrator == 1 else "wavefront",
+                "rng": "pcg3d_reference" if args.rng == 0 else "philox", "math": "fast (CUDA f32 libm)" if args.math == 0 else "exact",
+                "parallelism": f"frames sharded over {world} GPU(s), one NCCL reduce of the spectral accumulation buffers"},
         "mrays_per_s": rays / (total_ms * 1e-3) / 1e6,
         "rays_per_sample": rays / samples,
         "reduce_ms": reduce_ms, "wall_s_timed_region": wall,
         "clocks": clk,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "what": "per step: srt_render_frames + srt_resolve_rgba_f32 into pinned host memory"},
+                "what": "srt_render_progressive: per step F frames + the RGBA8 image of the frames so far (FrameUpdate, main.rs:1343-1348) "
+                        "resolved on the device, copied to pinned host memory on a second stream and handed to a host callback; "
+                        "at the end srt_resolve_rgba_f32 into pinned host memory (amortised over the steps in d2h)",
+                "host_checksum": checksum[0]},
         "gpu_launches": int(launches),
         "roofline": roofline,
-        "roofline_fp32": fp32,
+        "roofline_hbm": roofline_hbm,
         "cpu_baseline": cpu,
         "cpu_baseline_tight": cpu_tight,
         "rmse": rmse,
     }
+    line.update(extras)
     emit(line)
     r.close()
     if world > 1:

@@ -94,9 +94,10 @@ enum { SRT_RNG_PCG3D_REFERENCE = 0, SRT_RNG_PHILOX = 1 };
 enum { SRT_MATH_FAST = 0, SRT_MATH_EXACT = 1 };
 enum { SRT_ACCEL_AUTO = 0, SRT_ACCEL_LINEAR = 1, SRT_ACCEL_BVH = 2 };
 /* WAVEFRONT: per-stage kernels over SoA path pools in HBM, compaction between bounces.  RESIDENT: one
- * persistent kernel, a path stays in its lane with its state in registers / shared memory (n_lambda == 32
- * only, otherwise the wavefront is used).  AUTO: resident for linear-scan scenes, wavefront for BVH scenes
- * (latency-bound traversal wants the wavefront's higher occupancy). */
+ * persistent kernel, a path stays in its lane with its state in registers / shared memory (every legal n_lambda
+ * for linear-scan scenes; BVH scenes at the default n_lambda = 32 only -- otherwise the wavefront is used).
+ * AUTO: resident for linear-scan scenes, wavefront for BVH scenes (latency-bound traversal wants the wavefront's
+ * higher occupancy). */
 enum { SRT_INTEGRATOR_WAVEFRONT = 0, SRT_INTEGRATOR_RESIDENT = 1, SRT_INTEGRATOR_AUTO = 2 };
 
 /* Per-render constants: RaytracingUniforms minus the scene vectors
@@ -170,8 +171,19 @@ int srt_render_frames(srt_ctx* ctx, uint32_t first_frame, uint32_t n_frames);
 typedef int (*srt_progress_fn)(void* user, uint32_t frames_done, uint32_t frames_total, const uint8_t* rgba8);
 int srt_render_progressive(srt_ctx* ctx, uint32_t first_frame, uint32_t n_frames, uint32_t frames_per_update,
                            int want_preview, srt_progress_fn callback, void* user);
-/* Request that a running / the next srt_render_frames / srt_render_progressive stops at a batch boundary. */
+/* Request that a running / the next srt_render_frames / srt_render_progressive stops.  May be called from another
+ * thread while a render call is in progress.  The render stops at a FRAME boundary: frames already started are
+ * completed (the paths in flight are traced to their end), no further frame is begun, srt_frames_accumulated counts
+ * exactly the frames the buffer holds, and the call returns SRT_ERR_ABORTED.  (The resident integrator renders a
+ * call's frames in one launch: the flag is looked at between calls / batches there.) */
 int srt_abort(srt_ctx* ctx);
+/* Bit-reproducible accumulation.  Radiance is added to the buffer with f32 atomics; when one launch spans several
+ * frames, different warps add to the same pixel record in an order that changes from run to run, so images agree
+ * only to f32 rounding (a few ulp of the sum).  With deterministic = 1 srt_render_frames renders frame by frame (one
+ * launch per frame): a pixel record then receives its terms in frame order, within a frame in bounce order, and two
+ * runs -- or an interrupted and resumed run -- give identical bits.  Costs the tail of one launch per frame
+ * (a few percent at 1080p).  Default 0. */
+int srt_set_deterministic(srt_ctx* ctx, int on);
 /* Zero the accumulation buffer and the frame count (a fresh CustomImage::new). */
 int srt_clear(srt_ctx* ctx);
 uint64_t srt_frames_accumulated(const srt_ctx* ctx);
@@ -197,16 +209,27 @@ int srt_get_params(const srt_ctx* ctx, srt_params* out);
  * count and the accumulation buffer (FNV-1a checksums; written aside and renamed).  load restores buffer and frame
  * count into a context of the SAME scene and constants (else SRT_ERR_INVALID_ARGUMENT; accel / integrator / device /
  * pool size may differ -- they do not change the image).  open builds a new context from the file alone (device = -1:
- * current device); render further frames with srt_render_frames(ctx, srt_frames_accumulated(ctx), n).
+ * current device); render further frames with srt_render_frames(ctx, srt_frames_accumulated(ctx), n).  A resumed render
+ * equals the uninterrupted one bit for bit in deterministic mode (srt_set_deterministic) or with one frame per call;
+ * otherwise to f32 rounding of the sums.
  * (The reference keeps the image in memory only and lists scene saving as a TODO, main.rs:73.) */
 int srt_checkpoint_save(srt_ctx* ctx, const char* path);
 int srt_checkpoint_load(srt_ctx* ctx, const char* path);
 int srt_checkpoint_open(const char* path, int32_t device, srt_ctx** out);
 
 /* Sum the accumulation buffers of n contexts (one per device, same image size)
- * into ctxs[0] with NCCL (single-process multi-device); ctxs[0]'s frame count
- * becomes the total.  Lives in libsrt_nccl.so. */
+ * into ctxs[0] with NCCL (single-process multi-device).  Afterwards ctxs[0] holds
+ * the whole render -- its frame count is the sum of all n frame counts -- and
+ * ctxs[1..] are cleared (empty image, frame count 0), so the call can be repeated
+ * after further srt_render_frames rounds without counting radiance twice.  The
+ * NCCL communicators are created on the first call for a given set of devices and
+ * reused; srt_reduce_shutdown destroys them.  srt_reduce_last_ms: device time of
+ * the last reduce (CUDA events on ctxs[0]'s stream).  These four live in
+ * libsrt_nccl.so. */
 int srt_reduce(srt_ctx* const* ctxs, uint32_t n);
+void srt_reduce_shutdown(void);
+float srt_reduce_last_ms(void);
+const char* srt_reduce_last_error(void);
 
 /* mean spectrum -> XYZ -> RGB (get_rgb_early, spectrum.rs:238-261), alpha = 1:
  * out = W*H*4 f32, the layout of CustomImage.data (custom_image.rs:9-13). */

@@ -1,5 +1,7 @@
 """Summarise an .ncu-rep (read here, no GPU needed): headline metrics, stall reasons, opcode mix and the
-most-sampled SASS instructions of the first captured launch.  Usage: ncu_summary.py report.ncu-rep [out.txt]"""
+most-sampled SASS instructions of the first captured launch.
+Usage: ncu_summary.py report.ncu-rep [out.txt] [--samples N]   (N = samples the captured launch rendered; bench.py turns the
+summary's DRAM bytes into bytes per sample with it)"""
 import collections
 import csv
 import io
@@ -7,8 +9,14 @@ import re
 import subprocess
 import sys
 
-rep = sys.argv[1]
-out = open(sys.argv[2], "w") if len(sys.argv) > 2 else sys.stdout
+argv = list(sys.argv[1:])
+samples = None
+if "--samples" in argv:
+    i = argv.index("--samples")
+    samples = int(argv[i + 1])
+    del argv[i:i + 2]
+rep = argv[0]
+out = open(argv[1], "w") if len(argv) > 1 else sys.stdout
 
 
 def ncu(*args):
@@ -33,12 +41,17 @@ want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__warps_eligible.avg.per_cycle_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
         "l1tex__t_sector_hit_rate.pct", "sm__cycles_active.avg", "smsp__cycles_active.avg",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "sm__icc_request_hit_rate.pct", "idc__request_cycles_active.avg.pct_of_peak_sustained_elapsed"]
 for r in rows[2:]:
     P("=== kernel:", r[hdr.index("Kernel Name")][:110])
+    if samples:
+        P(f"  {'samples_in_launch':72s} {samples:>18d}")
     for k in want:
         if k in hdr:
             P(f"  {k:72s} {r[hdr.index(k)]:>18s} {units[hdr.index(k)]}")
+    if samples and "smsp__inst_executed.sum" in hdr:
+        P(f"  {'warp_instructions_per_sample':72s} {float(r[hdr.index('smsp__inst_executed.sum')].replace(',', '')) / samples:>18.1f}")
     st = []
     for i, k in enumerate(hdr):
         if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio"):

@@ -20,7 +20,7 @@ EXPORTS = (
     "srt_accum_device_ptr", "srt_stream", "srt_device", "srt_read_accum", "srt_write_accum",
     "srt_resolve_rgba_f32", "srt_resolve_rgba_u8", "srt_resolve_rgba_f32_device", "srt_primary_ids",
     "srt_spectrum_to_rgb", "srt_get_counters", "srt_reset_counters", "srt_last_render_stats",
-    "srt_set_profiling", "srt_last_stage_times",
+    "srt_set_profiling", "srt_last_stage_times", "srt_set_deterministic",
 )
 
 SRT_OK = 0
@@ -132,6 +132,7 @@ def lib() -> C.CDLL:
     L.srt_reset_counters.argtypes = [vp]
     L.srt_last_render_stats.argtypes = [vp, fp, C.POINTER(u64)]
     L.srt_set_profiling.argtypes = [vp, C.c_int]
+    L.srt_set_deterministic.argtypes = [vp, C.c_int]
     L.srt_last_stage_times.argtypes = [vp, fp, C.POINTER(u64)]
     _lib = L
     return L

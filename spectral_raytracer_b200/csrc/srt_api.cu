@@ -12,20 +12,51 @@
 // CUDA device every entry point fails with SRT_ERR_CUDA.
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
 
+#include <new>
+#include <stdexcept>
+
 #include "../../include/srt.h"
 #include "srt_kernels.cuh"
+#include "srt_resident.h"
 
 using namespace srt;
 
 namespace {
 
 thread_local std::string g_last_error;
+
+// The ABI structs are mirrored field by field on the caller's side (#[repr(C)] in ffi/src/lib.rs, ctypes in
+// _native.py): pin their layout here, where a change of include/srt.h gets compiled.
+#define SRT_LAYOUT(type, field, off) static_assert(offsetof(type, field) == (off), #type "." #field " moved")
+static_assert(sizeof(srt_object) == 92 && alignof(srt_object) == 4, "srt_object layout");
+SRT_LAYOUT(srt_object, min, 0); SRT_LAYOUT(srt_object, max, 12); SRT_LAYOUT(srt_object, kind, 24); SRT_LAYOUT(srt_object, center, 28);
+SRT_LAYOUT(srt_object, dims, 40); SRT_LAYOUT(srt_object, rot, 52); SRT_LAYOUT(srt_object, material, 88);
+static_assert(sizeof(srt_material) == 24 && alignof(srt_material) == 4, "srt_material layout");
+SRT_LAYOUT(srt_material, metallicness, 0); SRT_LAYOUT(srt_material, roughness, 4); SRT_LAYOUT(srt_material, reflectance, 8);
+SRT_LAYOUT(srt_material, transmissive, 12); SRT_LAYOUT(srt_material, ior_a, 16); SRT_LAYOUT(srt_material, ior_b, 20);
+static_assert(sizeof(srt_light) == 16 && alignof(srt_light) == 4, "srt_light layout");
+SRT_LAYOUT(srt_light, position, 0); SRT_LAYOUT(srt_light, spectrum, 12);
+static_assert(sizeof(srt_camera) == 40 && alignof(srt_camera) == 4, "srt_camera layout");
+SRT_LAYOUT(srt_camera, position, 0); SRT_LAYOUT(srt_camera, direction, 12); SRT_LAYOUT(srt_camera, up, 24); SRT_LAYOUT(srt_camera, fov_y_deg, 36);
+static_assert(sizeof(srt_params) == 60 && alignof(srt_params) == 4, "srt_params layout");
+SRT_LAYOUT(srt_params, width, 0); SRT_LAYOUT(srt_params, height, 4); SRT_LAYOUT(srt_params, n_lambda, 8); SRT_LAYOUT(srt_params, lambda_min, 12);
+SRT_LAYOUT(srt_params, lambda_max, 16); SRT_LAYOUT(srt_params, max_bounces, 20); SRT_LAYOUT(srt_params, intended_frames, 24);
+SRT_LAYOUT(srt_params, rng_mode, 28); SRT_LAYOUT(srt_params, math_mode, 32); SRT_LAYOUT(srt_params, accel, 36); SRT_LAYOUT(srt_params, integrator, 40);
+SRT_LAYOUT(srt_params, device, 44); SRT_LAYOUT(srt_params, pool_paths, 48); SRT_LAYOUT(srt_params, philox_seed_lo, 52); SRT_LAYOUT(srt_params, philox_seed_hi, 56);
+static_assert(sizeof(srt_counters) == 13 * 8 && alignof(srt_counters) == 8, "srt_counters layout");
+SRT_LAYOUT(srt_counters, samples, 0); SRT_LAYOUT(srt_counters, rays_primary, 8); SRT_LAYOUT(srt_counters, rays_continuation, 16);
+SRT_LAYOUT(srt_counters, rays_shadow, 24); SRT_LAYOUT(srt_counters, hits, 32); SRT_LAYOUT(srt_counters, self_hits, 40);
+SRT_LAYOUT(srt_counters, misses, 48); SRT_LAYOUT(srt_counters, lit, 56); SRT_LAYOUT(srt_counters, spec_hits, 64);
+SRT_LAYOUT(srt_counters, spec_dropped, 72); SRT_LAYOUT(srt_counters, iterations, 80); SRT_LAYOUT(srt_counters, kernel_launches, 88);
+SRT_LAYOUT(srt_counters, shadow_skipped, 96);
+#undef SRT_LAYOUT
 
 // CIE 1931 2-degree standard observer, 5 nm steps, 380..780 nm: the data of
 // WAVELENGTH_TO_XYZ_TABLE (spectrum.rs:688-770).
@@ -254,8 +285,13 @@ struct srt_ctx {
     SceneParams scene{};
     int device = 0;
     bool use_bvh = false;
-    bool resident = false;       // SRT_INTEGRATOR_RESIDENT and n_lambda == 32
-    uint32_t resident_grid = 0;
+    bool resident = false;       // the resident integrator runs this scene (else the wavefront)
+    ResidentKernel resident_kernel{};  // the instantiation chosen for the scene (srt_resident.h)
+    size_t resident_smem = 0;
+    uint32_t resident_grid = 0;  // SMs x blocks the occupancy calculator says are resident
+    bool deterministic = false;  // srt_set_deterministic: one launch per frame
+    uint32_t resolve_pixels = 0;  // k_resolve: pixels (= threads) per block and its dynamic shared memory
+    size_t resolve_smem = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     uint32_t capacity = 0;
@@ -311,6 +347,23 @@ int fail(srt_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->error = msg;
     g_last_error = msg;
     return code;
+}
+
+// "Nothing unwinds across this boundary" (srt.h): every entry point that can allocate on the host runs its body
+// through this.
+template <class F>
+int guarded(srt_ctx* c, F&& body) noexcept {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(c, SRT_ERR_CUDA, "out of host memory");
+    } catch (const std::length_error&) {
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, "a size in the request is too large");
+    } catch (const std::exception& e) {
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, std::string("internal error: ") + e.what());
+    } catch (...) {
+        return fail(c, SRT_ERR_INVALID_ARGUMENT, "internal error");
+    }
 }
 
 #define CUDA_TRY(ctx, expr)                                                                        \
@@ -394,40 +447,15 @@ void launch_shade(srt_ctx* c, int parity, unsigned long long total, uint32_t fir
 #endif
 }
 
-template <class Accel, int FEAT>
-void launch_resident_feat(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
-    const bool exact = c->params.math_mode == SRT_MATH_EXACT, philox = c->params.rng_mode == SRT_RNG_PHILOX;
+// The resident kernel is specialised on what the scene contains (c->features, kFeat* bits: lobes its materials
+// can produce, primitive kinds present) and on the spectral width: srt_create picked the smallest instantiated
+// superset (srt_resident.h) -- a Cornell-box-like scene (diffuse, plain + rotated boxes) runs a kernel without
+// specular / transmissive / sphere code.
+cudaError_t launch_resident(srt_ctx* c, unsigned long long total, uint32_t first_frame) {
     unsigned long long* next = reinterpret_cast<unsigned long long*>(c->ctl);
     float4* acc = reinterpret_cast<float4*>(c->accum);
-    const size_t smem = resident_smem_bytes(c->scene, Accel::kStageInShared, 8);
-#define SRT_RES(E, P)                                                                                                        \
-    do {                                                                                                                     \
-        if (smem > 48 * 1024)                                                                                                \
-            cudaFuncSetAttribute(k_resident<Accel, E, P, 8, FEAT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-        k_resident<Accel, E, P, 8, FEAT><<<grid, kResidentBlock, smem, c->stream>>>(c->scene, next, total, first_frame, acc, \
-                                                                                  c->counters);                             \
-    } while (0)
-#ifdef SRT_DEV_MINIMAL
-    (void)exact; (void)philox;
-    SRT_RES(false, false);
-#else
-    if (exact && philox) SRT_RES(true, true);
-    else if (exact) SRT_RES(true, false);
-    else if (philox) SRT_RES(false, true);
-    else SRT_RES(false, false);
-#endif
-#undef SRT_RES
-}
-// The resident kernel is specialised on what the scene contains (c->features, kFeat* bits: lobes its materials
-// can produce, primitive kinds present): the smallest instantiated superset is launched -- a Cornell-box-like
-// scene (diffuse, plain + rotated boxes) runs a kernel without specular / transmissive / sphere code.
-template <class Accel>
-void launch_resident(srt_ctx* c, unsigned long long total, uint32_t first_frame, dim3 grid) {
-    constexpr int kCornellLike = kFeatRot, kDefaultLike = kFeatSpecular | kFeatSphere;
-    const int need = c->features;
-    if (Accel::kStageInShared && (need & ~kCornellLike) == 0) launch_resident_feat<Accel, kCornellLike>(c, total, first_frame, grid);
-    else if (Accel::kStageInShared && (need & ~kDefaultLike) == 0) launch_resident_feat<Accel, kDefaultLike>(c, total, first_frame, grid);
-    else launch_resident_feat<Accel, kFeatAll>(c, total, first_frame, grid);
+    void* args[] = {&c->scene, &next, &total, &first_frame, &acc, &c->counters};
+    return cudaLaunchKernel(c->resident_kernel.fn, dim3(c->resident_grid), dim3(kResidentBlock), args, c->resident_smem, c->stream);
 }
 
 // One wavefront iteration: generate -> extend -> shade.  Grids cover the whole
@@ -484,7 +512,7 @@ int resolve(srt_ctx* c, bool want_f32, bool want_u8) {
     if (want_f32 && !c->rgba_f32) CUDA_TRY(c, cudaMalloc(&c->rgba_f32, (size_t)npix * sizeof(float4)));
     if (want_u8 && !c->rgba_u8) CUDA_TRY(c, cudaMalloc(&c->rgba_u8, (size_t)npix * sizeof(uchar4)));
     float frames = c->frames_accumulated ? (float)c->frames_accumulated : 1.0f;
-    k_resolve<<<(npix + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->accum, c->weights, npix, c->scene.n_lambda,
+    k_resolve<<<(npix + c->resolve_pixels - 1) / c->resolve_pixels, c->resolve_pixels, c->resolve_smem, c->stream>>>(c->accum, c->weights, npix, c->scene.n_lambda,
                                                                       c->weights_used, frames,
                                                                       want_f32 ? c->rgba_f32 : nullptr,
                                                                       want_u8 ? c->rgba_u8 : nullptr);
@@ -513,7 +541,7 @@ int srt_device_count(void) {
 
 const char* srt_last_error(const srt_ctx* ctx) { return ctx ? ctx->error.c_str() : g_last_error.c_str(); }
 
-int srt_create(const srt_params* params, const srt_camera* camera, const srt_object* objects, uint32_t n_objects,
+static int srt_create_body(const srt_params* params, const srt_camera* camera, const srt_object* objects, uint32_t n_objects,
                const srt_material* materials, uint32_t n_materials, const srt_light* lights, uint32_t n_lights,
                const float* spectra, uint32_t n_spectra, srt_ctx** out) {
     if (!out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "out is null");
@@ -561,7 +589,12 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
     }
     if (device >= n_dev) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "device ordinal out of range");
 
-    srt_ctx* c = new srt_ctx();
+    // (owned until the context is handed out: an exception or an early return frees what was allocated so far)
+    struct Owner {
+        srt_ctx* c;
+        ~Owner() { if (c) free_ctx(c); }
+    } owner{new srt_ctx()};
+    srt_ctx* c = owner.c;
     c->params = *params;
     c->device = device;
     c->in_camera = *camera;
@@ -571,19 +604,23 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
     c->in_spectra.assign(spectra, spectra + (size_t)n_spectra * params->n_lambda);
     c->in_n_spectra = n_spectra;
     DeviceGuard guard(device);
-    if (!guard.ok) {
-        delete c;
-        return fail(nullptr, SRT_ERR_CUDA, "cudaSetDevice failed");
-    }
-    auto bail = [&](int code, const std::string& msg) {
-        free_ctx(c);
-        return fail(nullptr, code, msg);
-    };
+    if (!guard.ok) return fail(nullptr, SRT_ERR_CUDA, "cudaSetDevice failed");
+    auto bail = [&](int code, const std::string& msg) { return fail(nullptr, code, msg); };
 #define CREATE_TRY(expr)                                                                    \
     do {                                                                                    \
         cudaError_t e_ = (expr);                                                            \
         if (e_ != cudaSuccess) return bail(SRT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_)); \
     } while (0)
+
+    // the library carries sm_100a SASS only (no PTX): say so instead of failing later with "no kernel image"
+    {
+        int major = 0, minor = 0;
+        CREATE_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+        CREATE_TRY(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device));
+        if (major != 10)
+            return bail(SRT_ERR_CUDA, "device " + std::to_string(device) + " has compute capability " + std::to_string(major) + "." +
+                                          std::to_string(minor) + ": this library's kernels are built for sm_100a (B200) only");
+    }
 
     SceneParams& sp = c->scene;
     const uint32_t nl = params->n_lambda, nl4 = nl / 4;
@@ -662,6 +699,8 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
                                    (params->accel == SRT_ACCEL_AUTO && n_objects > (uint32_t)kMaxConstObjects));
     if (!c->use_bvh && n_objects > (uint32_t)kMaxConstObjects)
         return bail(SRT_ERR_UNSUPPORTED, "linear scan supports at most 64 objects; use SRT_ACCEL_AUTO or SRT_ACCEL_BVH");
+    if (c->use_bvh && (uint64_t)n_objects * 2 >= (1ull << 24))
+        return bail(SRT_ERR_UNSUPPORTED, "more than 2^23 - 1 objects (the BVH traversal packs node indices into 24 bits)");
     if (c->use_bvh) {
         std::vector<DevBvhNode> nodes;
         std::vector<uint32_t> prim_index;
@@ -729,6 +768,10 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         sp.frames = c->frames;
     }
     // colour weights
+    c->resolve_pixels = (uint32_t)resolve_block_pixels(nl);
+    c->resolve_smem = resolve_smem_bytes(nl);
+    if (c->resolve_smem > 48 * 1024)
+        CREATE_TRY(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->resolve_smem));
     {
         std::vector<float> w;
         c->weights_used = build_rgb_weights(nl, params->lambda_min, params->lambda_max, w);
@@ -736,14 +779,42 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
         CREATE_TRY(cudaMemcpy(c->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
 
-    // integrator: the resident kernel keeps the throughput in registers and is instantiated for the
-    // default spectral width (NBR_OF_SPECTRUM_SAMPLES_DEFAULT = 32, main.rs:32); other widths use the wavefront
-    c->resident = nl4 == 8 && (params->integrator == SRT_INTEGRATOR_RESIDENT ||
-                               (params->integrator == SRT_INTEGRATOR_AUTO && !c->use_bvh));
+    // integrator: AUTO = resident for linear-scan scenes, wavefront for BVH scenes.  The resident kernel exists for
+    // every legal spectral width (powers of two with compile-time loops, the widths in between with guarded loops).
     {
         cudaDeviceProp prop;
         CREATE_TRY(cudaGetDeviceProperties(&prop, device));
-        c->resident_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)kResidentBlocksPerSm;
+        const bool want = params->integrator == SRT_INTEGRATOR_RESIDENT || (params->integrator == SRT_INTEGRATOR_AUTO && !c->use_bvh);
+        if (want) {
+            const bool exact = params->math_mode == SRT_MATH_EXACT, philox = params->rng_mode == SRT_RNG_PHILOX;
+            const int cap = nl4 <= 2 ? 2 : nl4 <= 4 ? 4 : nl4 <= 8 ? 8 : nl4 <= 16 ? 16 : 32;
+            const bool partial = (uint32_t)cap != nl4;
+            ResidentKernel k;
+            switch (cap) {
+#ifndef SRT_DEV_ONLY_NL8
+            case 2: k = resident_kernel_nl2(c->use_bvh, exact, philox, c->features, partial); break;
+            case 4: k = resident_kernel_nl4(c->use_bvh, exact, philox, c->features, partial); break;
+            case 16: k = resident_kernel_nl16(c->use_bvh, exact, philox, c->features, partial); break;
+            case 32: k = resident_kernel_nl32(c->use_bvh, exact, philox, c->features, partial); break;
+#endif
+            case 8: k = resident_kernel_nl8(c->use_bvh, exact, philox, c->features, partial); break;
+            default: break;
+            }
+            if (k.fn) {
+                c->resident_kernel = k;
+                c->resident_smem = resident_smem_bytes(sp, !c->use_bvh, k.cap);
+                if (c->resident_smem > 48 * 1024)
+                    CREATE_TRY(cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->resident_smem));
+                // persistent grid: exactly the blocks that are resident at once (occupancy calculator: registers and
+                // the scene-dependent shared memory), so no block waits for a slot while others hold all the samples
+                int per_sm = 0;
+                CREATE_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k.fn, kResidentBlock, c->resident_smem));
+                if (per_sm > 0) {
+                    c->resident = true;
+                    c->resident_grid = (uint32_t)prop.multiProcessorCount * (uint32_t)std::min(per_sm, k.min_blocks);
+                }
+            }
+        }
     }
     // path pools + accumulation buffer
     uint32_t cap = params->pool_paths ? params->pool_paths : (1u << 21);
@@ -768,6 +839,7 @@ int srt_create(const srt_params* params, const srt_camera* camera, const srt_obj
     CREATE_TRY(cudaMemset(c->accum, 0, c->accum_floats * sizeof(float)));
     CREATE_TRY(cudaDeviceSynchronize());
 #undef CREATE_TRY
+    owner.c = nullptr;
     *out = c;
     return SRT_OK;
 }
@@ -783,7 +855,30 @@ int srt_abort(srt_ctx* ctx) {
 // wait = false (resident integrator only): return once the work is queued on the context's stream
 static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, bool wait);
 
-int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) { return render_frames_impl(c, first_frame, n_frames, true); }
+int srt_render_frames(srt_ctx* c, uint32_t first_frame, uint32_t n_frames) {
+    return guarded(c, [&] {
+        if (!c || !c->deterministic || n_frames <= 1) return render_frames_impl(c, first_frame, n_frames, true);
+        // deterministic mode: one launch per frame, so every pixel record receives its radiance terms in frame
+        // order (within a frame all terms of a pixel come from one path, in bounce order)
+        float ms = 0.0f;
+        uint64_t launches = 0;
+        for (uint32_t f = 0; f < n_frames; ++f) {
+            const int rc = render_frames_impl(c, first_frame + f, 1, true);
+            ms += c->last_ms;
+            launches += c->last_launches;
+            if (rc) return rc;
+        }
+        c->last_ms = ms;
+        c->last_launches = launches;
+        return (int)SRT_OK;
+    });
+}
+
+int srt_set_deterministic(srt_ctx* c, int on) {
+    if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
+    c->deterministic = on != 0;
+    return SRT_OK;
+}
 
 static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, bool wait) {
     if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
@@ -827,9 +922,7 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
             c->abort_flag = 0;
             return fail(c, SRT_ERR_ABORTED, "render aborted");
         }
-        dim3 grid(c->resident_grid);
-        if (c->use_bvh) launch_resident<AccelBvh>(c, total, first_frame, grid);
-        else launch_resident<AccelLinear>(c, total, first_frame, grid);
+        CUDA_TRY(c, launch_resident(c, total, first_frame));
         c->launches += 1;
         CUDA_TRY(c, cudaGetLastError());
         c->last_launches = c->launches - launches_before;
@@ -844,16 +937,23 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
     // The number of iterations depends on the path lengths, so the host launches
     // them in chunks and looks at the control block between chunks (one 32-byte
     // copy); iterations launched after the work ran out exit immediately.
+    // srt_abort() during the call: no further FRAME is started -- the sample range is cut at the next frame
+    // boundary at or above what has been generated so far -- but the paths in flight are traced to their end, so
+    // the buffer holds whole frames only and frames_accumulated counts exactly those.
     int parity = 0;
     bool done = false, aborted = false;
     uint32_t chunk = 8;
+    unsigned long long goal = total;   // samples this call will generate (shrinks on abort)
+    unsigned long long generated = 0;  // next_sample as of the last look at the control block
     while (!done) {
-        if (c->abort_flag) {
+        if (c->abort_flag && !aborted) {
             aborted = true;
-            break;
+            goal = (generated + c->scene.npix - 1) / c->scene.npix * c->scene.npix;
+            if (goal > total) goal = total;
+            if (goal == 0) break;  // nothing was started
         }
         for (uint32_t k = 0; k < chunk; ++k) {
-            launch_iteration(c, parity, total, first_frame);
+            launch_iteration(c, parity, goal, first_frame);
             parity ^= 1;
         }
         CUDA_TRY(c, cudaGetLastError());
@@ -861,11 +961,12 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         if (c->profiling) prof_collect(c);
         const PoolCtl& now = c->h_ctl[parity];
-        done = now.count == 0 && now.next_sample >= total;
+        generated = now.next_sample;
+        done = now.count == 0 && now.next_sample >= goal;
         if (!done) {
             // remaining work in pool-fills, to size the next chunk (at least the tail of
             // max_bounces iterations, at most 64 launches between checks)
-            unsigned long long remaining = total - std::min<unsigned long long>(total, now.next_sample);
+            unsigned long long remaining = goal - std::min<unsigned long long>(goal, now.next_sample);
             uint32_t est = (uint32_t)std::min<unsigned long long>(64, remaining / c->capacity + 1);
             chunk = std::max(est, remaining ? 4u : std::min(16u, c->scene.max_bounces + 1));
         }
@@ -874,11 +975,11 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
     CUDA_TRY(c, cudaEventSynchronize(c->ev_end));
     CUDA_TRY(c, cudaEventElapsedTime(&c->last_ms, c->ev_begin, c->ev_end));
     c->last_launches = c->launches - launches_before;
+    c->frames_accumulated += goal / c->scene.npix;
     if (aborted) {
         c->abort_flag = 0;
         return fail(c, SRT_ERR_ABORTED, "render aborted");
     }
-    c->frames_accumulated += n_frames;
     return SRT_OK;
 }
 
@@ -886,7 +987,7 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
 // image is resolved to RGBA8 on the render stream, copied to pinned host memory on a second stream while
 // batch k+1 renders, and handed to the callback once the copy is done -- so the GPU never waits for the host,
 // and an abort requested in update k takes effect after batch k+1 (which is already running).
-int srt_render_progressive(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frames_per_update, int want_preview,
+static int srt_render_progressive_body(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frames_per_update, int want_preview,
                            srt_progress_fn callback, void* user) {
     if (!c) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "ctx is null");
     if (n_frames == 0) return SRT_OK;
@@ -924,14 +1025,23 @@ int srt_render_progressive(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, 
     };
     uint32_t k = 0;
     for (; k < n_updates && !abort_requested; ++k) {
-        const uint32_t n = std::min(frames_per_update, n_frames - queued);
+        uint32_t n = std::min(frames_per_update, n_frames - queued);
         // resident integrator: queued asynchronously; wavefront: the host drives its iterations, returns when done
+        const uint64_t before = c->frames_accumulated;
         rc = render_frames_impl(c, first_frame + queued, n, !c->resident);
+        if (rc == SRT_ERR_ABORTED) {
+            // srt_abort() landed during (or before) this batch: the frames it completed stay accumulated and are
+            // reported like any other update, then the render stops
+            n = (uint32_t)(c->frames_accumulated - before);
+            abort_requested = true;
+            rc = SRT_OK;
+            if (n == 0) break;
+        }
         if (rc) break;
         queued += n;
         if (preview) {
             const float frames = c->frames_accumulated ? (float)c->frames_accumulated : 1.0f;
-            k_resolve<<<(npix + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(c->accum, c->weights, npix, c->scene.n_lambda,
+            k_resolve<<<(npix + c->resolve_pixels - 1) / c->resolve_pixels, c->resolve_pixels, c->resolve_smem, c->stream>>>(c->accum, c->weights, npix, c->scene.n_lambda,
                                                                               c->weights_used, frames, nullptr, c->prev_d[k & 1]);
             c->launches += 1;
             cudaEventRecord(c->ev_resolved[k & 1], c->stream);
@@ -1077,10 +1187,24 @@ int read_ckpt_scene(srt_ctx* c, FILE* f, CkptFile& k) {
     if (k.h.sizeof_params != sizeof(srt_params) || k.h.sizeof_camera != sizeof(srt_camera) || k.h.sizeof_object != sizeof(srt_object) ||
         k.h.sizeof_material != sizeof(srt_material) || k.h.sizeof_light != sizeof(srt_light))
         return fail(c, SRT_ERR_UNSUPPORTED, "checkpoint: written by a different ABI");
-    if (k.h.n_lambda == 0 || k.h.n_lambda > (uint32_t)kMaxLambda || k.h.n_objects > (1u << 24) || k.h.n_materials > (1u << 24) ||
+    // the same limits srt_create enforces, before anything is sized from the header ...
+    if (k.h.n_lambda == 0 || k.h.n_lambda % 8 != 0 || k.h.n_lambda > (uint32_t)kMaxLambda || k.h.width == 0 || k.h.height == 0 ||
+        (uint64_t)k.h.width * k.h.height > 0x7fffffffull || k.h.n_objects > (1u << 24) || k.h.n_materials > (1u << 24) ||
         k.h.n_lights > (uint32_t)kMaxLights || k.h.n_spectra > (1u << 24) ||
         k.h.payload_floats != (uint64_t)k.h.width * k.h.height * k.h.n_lambda)
         return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: inconsistent header");
+    // ... and the sizes it declares must be exactly what the file holds (a truncated or hostile file must not make
+    // this allocate gigabytes)
+    {
+        const uint64_t want = (uint64_t)sizeof(CkptHeader) + sizeof(srt_params) + sizeof(srt_camera) + (uint64_t)k.h.n_objects * sizeof(srt_object) +
+                              (uint64_t)k.h.n_materials * sizeof(srt_material) + (uint64_t)k.h.n_lights * sizeof(srt_light) +
+                              (uint64_t)k.h.n_spectra * k.h.n_lambda * sizeof(float) + k.h.payload_floats * sizeof(float);
+        const long pos = std::ftell(f);
+        if (pos < 0 || std::fseek(f, 0, SEEK_END) != 0) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: cannot seek");
+        const long size = std::ftell(f);
+        if (std::fseek(f, pos, SEEK_SET) != 0) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: cannot seek");
+        if (size < 0 || (uint64_t)size != want) return fail(c, SRT_ERR_INVALID_ARGUMENT, "checkpoint: file size does not match its header (truncated?)");
+    }
     k.objects.resize(k.h.n_objects);
     k.materials.resize(k.h.n_materials);
     k.lights.resize(k.h.n_lights);
@@ -1112,7 +1236,7 @@ int srt_get_params(const srt_ctx* c, srt_params* out) {
     return SRT_OK;
 }
 
-int srt_checkpoint_save(srt_ctx* c, const char* path) {
+static int srt_checkpoint_save_body(srt_ctx* c, const char* path) {
     if (!c || !path) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
     std::vector<float> buf(c->accum_floats);
     int rc = srt_read_accum(c, buf.data());
@@ -1155,7 +1279,7 @@ int srt_checkpoint_save(srt_ctx* c, const char* path) {
     return SRT_OK;
 }
 
-int srt_checkpoint_load(srt_ctx* c, const char* path) {
+static int srt_checkpoint_load_body(srt_ctx* c, const char* path) {
     if (!c || !path) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
     FileCloser fc{std::fopen(path, "rb")};
     if (!fc.f) return fail(c, SRT_ERR_INVALID_ARGUMENT, std::string("checkpoint: cannot open ") + path);
@@ -1169,7 +1293,7 @@ int srt_checkpoint_load(srt_ctx* c, const char* path) {
     return load_ckpt_payload(c, fc.f, k.h);
 }
 
-int srt_checkpoint_open(const char* path, int32_t device, srt_ctx** out) {
+static int srt_checkpoint_open_body(const char* path, int32_t device, srt_ctx** out) {
     if (!out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "out is null");
     *out = nullptr;
     if (!path) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
@@ -1223,7 +1347,7 @@ int srt_resolve_rgba_f32_device(srt_ctx* c, float* d_out) {
     return SRT_OK;
 }
 
-int srt_primary_ids(srt_ctx* c, uint32_t frame, int32_t* ids, float* t) {
+static int srt_primary_ids_body(srt_ctx* c, uint32_t frame, int32_t* ids, float* t) {
     if (!c || !ids) return fail(c, SRT_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(c->device);
     const uint32_t npix = c->scene.npix;
@@ -1251,7 +1375,7 @@ int srt_primary_ids(srt_ctx* c, uint32_t frame, int32_t* ids, float* t) {
     return SRT_OK;
 }
 
-int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max,
+static int srt_spectrum_to_rgb_body(const float* spectra, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max,
                         float* rgb) {
     if (!spectra || !rgb) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
     if (n_lambda == 0 || n_lambda % 8 != 0 || n_lambda > (uint32_t)kMaxLambda)
@@ -1287,7 +1411,7 @@ struct DevBuf {
 bool valid_nl(uint32_t nl) { return nl >= 8 && nl % 8 == 0 && nl <= (uint32_t)kMaxLambda; }
 }  // namespace
 
-int srt_spectra_resample(const float* in, uint32_t n, uint32_t n_old, uint32_t n_new, float* out) {
+static int srt_spectra_resample_body(const float* in, uint32_t n, uint32_t n_old, uint32_t n_new, float* out) {
     if (!in || !out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
     if (!valid_nl(n_old) || !valid_nl(n_new))
         return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
@@ -1323,7 +1447,7 @@ int srt_spectra_resample(const float* in, uint32_t n, uint32_t n_old, uint32_t n
     return SRT_OK;
 }
 
-int srt_spectra_radiance(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* radiance) {
+static int srt_spectra_radiance_body(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* radiance) {
     if (!in || !radiance) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
     if (!valid_nl(n_lambda)) return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
     if (n == 0) return SRT_OK;
@@ -1342,7 +1466,7 @@ int srt_spectra_radiance(const float* in, uint32_t n, uint32_t n_lambda, float l
     return SRT_OK;
 }
 
-int srt_spectra_normalize(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* out) {
+static int srt_spectra_normalize_body(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* out) {
     if (!in || !out) return fail(nullptr, SRT_ERR_INVALID_ARGUMENT, "null argument");
     if (!valid_nl(n_lambda)) return fail(nullptr, SRT_ERR_SPECTRUM_SAMPLES, "number of spectral samples must be a multiple of 8 in 8..=128");
     if (n == 0) return SRT_OK;
@@ -1371,7 +1495,9 @@ int srt_selftest_arith(uint64_t n, uint32_t seed, uint64_t* mismatches) {
     cudaError_t e = cudaMalloc(&d, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(d, 0, sizeof(unsigned long long));
     if (e == cudaSuccess) {
-        k_selftest_arith<<<148 * 8, kBlock>>>((unsigned long long)n, seed, d);
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        k_selftest_arith<<<sms * 8, kBlock>>>((unsigned long long)n, seed, d);
         e = cudaGetLastError();
     }
     unsigned long long h = 0;
@@ -1434,6 +1560,47 @@ int srt_last_stage_times(srt_ctx* c, float* ms, uint64_t* launches) {
         if (launches) launches[s] = c->stage_launches[s];
     }
     return SRT_OK;
+}
+
+// ---- the entry points whose bodies can allocate on the host (see guarded())
+int srt_create(const srt_params* params, const srt_camera* camera, const srt_object* objects, uint32_t n_objects, const srt_material* materials, uint32_t n_materials, const srt_light* lights, uint32_t n_lights, const float* spectra, uint32_t n_spectra, srt_ctx** out) {
+    return guarded(nullptr, [&] { return srt_create_body(params, camera, objects, n_objects, materials, n_materials, lights, n_lights, spectra, n_spectra, out); });
+}
+
+int srt_render_progressive(srt_ctx* c, uint32_t first_frame, uint32_t n_frames, uint32_t frames_per_update, int want_preview, srt_progress_fn callback, void* user) {
+    return guarded(c, [&] { return srt_render_progressive_body(c, first_frame, n_frames, frames_per_update, want_preview, callback, user); });
+}
+
+int srt_checkpoint_save(srt_ctx* c, const char* path) {
+    return guarded(c, [&] { return srt_checkpoint_save_body(c, path); });
+}
+
+int srt_checkpoint_load(srt_ctx* c, const char* path) {
+    return guarded(c, [&] { return srt_checkpoint_load_body(c, path); });
+}
+
+int srt_checkpoint_open(const char* path, int32_t device, srt_ctx** out) {
+    return guarded(nullptr, [&] { return srt_checkpoint_open_body(path, device, out); });
+}
+
+int srt_primary_ids(srt_ctx* c, uint32_t frame, int32_t* ids, float* t) {
+    return guarded(c, [&] { return srt_primary_ids_body(c, frame, ids, t); });
+}
+
+int srt_spectrum_to_rgb(const float* spectra, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* rgb) {
+    return guarded(nullptr, [&] { return srt_spectrum_to_rgb_body(spectra, n, n_lambda, lambda_min, lambda_max, rgb); });
+}
+
+int srt_spectra_resample(const float* in, uint32_t n, uint32_t n_old, uint32_t n_new, float* out) {
+    return guarded(nullptr, [&] { return srt_spectra_resample_body(in, n, n_old, n_new, out); });
+}
+
+int srt_spectra_radiance(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* radiance) {
+    return guarded(nullptr, [&] { return srt_spectra_radiance_body(in, n, n_lambda, lambda_min, lambda_max, radiance); });
+}
+
+int srt_spectra_normalize(const float* in, uint32_t n, uint32_t n_lambda, float lambda_min, float lambda_max, float* out) {
+    return guarded(nullptr, [&] { return srt_spectra_normalize_body(in, n, n_lambda, lambda_min, lambda_max, out); });
 }
 
 }  // extern "C"

@@ -238,6 +238,10 @@ class Renderer:
         return float(ms.value), int(k.value)
 
 
+    def set_deterministic(self, on: bool):
+        """srt_set_deterministic: one launch per frame, bit-reproducible accumulation."""
+        N.check(self._L.srt_set_deterministic(self._h, int(on)), self._h)
+
     def set_profiling(self, on: bool):
         N.check(self._L.srt_set_profiling(self._h, int(on)), self._h)
 
@@ -249,19 +253,34 @@ class Renderer:
         return [float(x) for x in ms], [int(x) for x in k]
 
 
-def reduce_contexts(renderers) -> None:
+_nccl_lib = None
+
+
+def nccl_lib():
+    """libsrt_nccl.so (srt_reduce and friends), loaded on first use."""
+    global _nccl_lib
+    if _nccl_lib is None:
+        import os
+        N.lib()
+        L = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrt_nccl.so"))
+        L.srt_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
+        L.srt_reduce_last_error.restype = C.c_char_p
+        L.srt_reduce_last_ms.restype = C.c_float
+        L.srt_reduce_shutdown.restype = None
+        _nccl_lib = L
+    return _nccl_lib
+
+
+def reduce_contexts(renderers) -> float:
     """srt_reduce (libsrt_nccl.so): sum the accumulation buffers of contexts living on DIFFERENT devices of this
-    process into renderers[0] with NCCL; renderers[0] then holds the whole render."""
-    import os
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsrt_nccl.so")
-    N.lib()
-    L = C.CDLL(path)
-    L.srt_reduce.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
-    L.srt_reduce_last_error.restype = C.c_char_p
+    process into renderers[0] with NCCL; renderers[0] then holds the whole render, the others are cleared.
+    Returns the device time of the reduce in ms."""
+    L = nccl_lib()
     arr = (C.c_void_p * len(renderers))(*[r._h for r in renderers])
     rc = L.srt_reduce(arr, len(renderers))
     if rc != N.SRT_OK:
         raise N.SrtError(rc, L.srt_reduce_last_error().decode())
+    return float(L.srt_reduce_last_ms())
 
 
 def spectrum_to_rgb(spectra: np.ndarray, lambda_min: float = 380.0, lambda_max: float = 780.0) -> np.ndarray:

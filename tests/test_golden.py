@@ -100,5 +100,15 @@ def test_srt_reduce_nccl_two_devices():
             first, count = frame_shard(0, n, rank, 2)
             r.render_frames(first, count)
         srt.reduce_contexts([a, b])
-        assert a.frames_accumulated == n
+        assert a.frames_accumulated == n and b.frames_accumulated == 0
+        assert not b.read_accum().any()          # the non-root context starts its next shard from an empty image
+        assert np.allclose(a.resolve_rgba_f32(), whole.resolve_rgba_f32(), rtol=1e-5, atol=1e-6)
+        # a second round (cached communicators): frames n .. 2n, every frame counted once
+        whole.render_frames(n, n)
+        for rank, r in enumerate((a, b)):
+            first, count = frame_shard(n, n, rank, 2)
+            r.render_frames(first, count)
+        ms = srt.reduce_contexts([a, b])
+        assert ms > 0.0
+        assert a.frames_accumulated == 2 * n and b.frames_accumulated == 0
         assert np.allclose(a.resolve_rgba_f32(), whole.resolve_rgba_f32(), rtol=1e-5, atol=1e-6)

@@ -18,7 +18,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "srt.h")).read()
     declared = set(re.findall(r"\b(srt_[a-z0-9_]+)\s*\(", header))
-    declared -= {"srt_reduce"}  # lives in libsrt_nccl.so (single-process multi-device NCCL)
+    in_nccl = {n for n in declared if n.startswith("srt_reduce")}  # live in libsrt_nccl.so (single-process multi-device NCCL)
+    assert in_nccl == {"srt_reduce", "srt_reduce_shutdown", "srt_reduce_last_ms", "srt_reduce_last_error"}
+    declared -= in_nccl
     lib = srt.native.lib()
     assert declared == set(srt.native.EXPORTS)
     for name in declared:
@@ -28,7 +30,8 @@ def test_library_exports_every_declared_symbol():
     for name in scenes.HOST_EXPORTS:
         assert hasattr(host, name), name
     nccl = C.CDLL(os.path.join(ROOT, "spectral_raytracer_b200", "libsrt_nccl.so"))
-    assert hasattr(nccl, "srt_reduce")
+    for name in in_nccl:
+        assert hasattr(nccl, name), name
 
 
 def test_abi_struct_sizes_match_header():
@@ -117,3 +120,56 @@ def test_validation_happens_before_the_device_is_touched():
     with pytest.raises(srt.SrtError) as e:
         srt.Renderer(flat, 8, 8, max_bounces=200)
     assert e.value.code == srt.native.SRT_ERR_UNSUPPORTED
+
+
+def test_header_is_plain_c11_and_layout_is_pinned(tmp_path):
+    """include/srt.h must compile as C (the Rust -sys crate / cgo / JNI side sees C, not C++), and the struct layout
+    the mirrors rely on is asserted from C as well (the C++ side asserts the same numbers in srt_api.cu)."""
+    import shutil
+    import subprocess
+    src = os.path.join(ROOT, "tests", "abi", "srt_h_c11.c")
+    cc = shutil.which("gcc") or shutil.which("cc")
+    assert cc, "no C compiler"
+    out = tmp_path / "srt_h_c11.o"
+    subprocess.check_call([cc, "-std=c11", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-c", src, "-o", str(out)])
+
+
+def _checkpoint_header(**over):
+    """A CkptHeader (srt_api.cu) with consistent sizes for a 4x2 image of 8 wavelengths and an empty scene."""
+    import struct
+    f = dict(magic=b"SRTCKPT1", version=1, header_bytes=96, width=4, height=2, n_lambda=8, n_objects=0, n_materials=0,
+             n_lights=0, n_spectra=0, sizeof_params=60, sizeof_camera=40, sizeof_object=92, sizeof_material=24, sizeof_light=16,
+             frames=1, scene_hash=0, payload_hash=0, payload_floats=4 * 2 * 8)
+    f.update(over)
+    return struct.pack("<8s15IQQQQ", f["magic"], f["version"], f["header_bytes"], f["width"], f["height"], f["n_lambda"],
+                       f["n_objects"], f["n_materials"], f["n_lights"], f["n_spectra"], f["sizeof_params"], f["sizeof_camera"],
+                       f["sizeof_object"], f["sizeof_material"], f["sizeof_light"], 0, f["frames"], f["scene_hash"],
+                       f["payload_hash"], f["payload_floats"])
+
+
+@pytest.mark.parametrize("case", ["truncated", "huge_spectra", "huge_image", "wrapping_image", "bad_lambda", "garbage"])
+def test_checkpoint_open_rejects_hostile_files_without_allocating(tmp_path, case):
+    """A truncated or hostile checkpoint must come back as an error code: sizes are validated against the file before
+    anything is allocated from them, and nothing unwinds across the C boundary (no GPU needed: all of this happens
+    before a device is touched)."""
+    lib = srt.native.lib()
+    body = b"\0" * (60 + 40)
+    if case == "truncated":
+        data = _checkpoint_header() + body            # payload missing
+    elif case == "huge_spectra":
+        data = _checkpoint_header(n_spectra=1 << 24, n_lambda=128, payload_floats=4 * 2 * 128) + body
+    elif case == "huge_image":
+        data = _checkpoint_header(width=1 << 20, height=1 << 20, payload_floats=(1 << 40) * 8) + body
+    elif case == "wrapping_image":
+        data = _checkpoint_header(width=0xFFFFFFFF, height=0xFFFFFFFF, payload_floats=((0xFFFFFFFF * 0xFFFFFFFF) * 8) & (2**64 - 1)) + body
+    elif case == "bad_lambda":
+        data = _checkpoint_header(n_lambda=12, payload_floats=4 * 2 * 12) + body + b"\0" * (4 * 2 * 12 * 4)
+    else:
+        data = os.urandom(4096)
+    path = tmp_path / "bad.ckpt"
+    path.write_bytes(data)
+    h = C.c_void_p()
+    rc = lib.srt_checkpoint_open(str(path).encode(), -1, C.byref(h))
+    assert rc in (srt.native.SRT_ERR_INVALID_ARGUMENT, srt.native.SRT_ERR_UNSUPPORTED) and not h.value
+    assert b"checkpoint" in lib.srt_last_error(None)
