@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -164,7 +165,8 @@ void build_bvh(const std::vector<DevObject>& objs, std::vector<DevBvhNode>& node
     std::vector<Task> stack;
     stack.push_back({0, 0, n, 0});
     constexpr int kBins = 16;
-    constexpr uint32_t kLeaf = 4;
+    uint32_t kLeaf = 4;
+    if (const char* e = std::getenv("SRT_BVH_LEAF")) kLeaf = std::max(1, std::min(8, std::atoi(e)));  // (developer knob)
     while (!stack.empty()) {
         Task t = stack.back();
         stack.pop_back();
