@@ -116,6 +116,16 @@ struct PathPool {
     float4* thr;    // [n_lambda4][capacity] path throughput
 };
 
+// Shadow-ray queue of the BVH wavefront: one region of `capacity` records per light, filled by k_shade and traced by
+// k_shadow (srt_kernels.cuh).  a = origin.xyz, |L|; b = direction.xyz, pixel (bits); c = the light's factors
+// (production math: c1*c2/|L|^2, -, -; exact math: |L|^2, c1, c2) and the path's slot in the next pool | scrub << 31 (bits).
+struct ShadowQueue {
+    float4* a = nullptr;
+    float4* b = nullptr;
+    float4* c = nullptr;
+    uint32_t* count = nullptr;  // [kMaxLights] records queued in this iteration (reset by k_generate)
+};
+
 // Double-buffered control block (see srt_kernels.cuh: iteration `it` reads
 // ctl[it&1] and builds ctl[(it+1)&1]).
 struct PoolCtl {

@@ -234,3 +234,34 @@ def test_deterministic_mode_is_bit_reproducible(integrator):
     with srt.Renderer(flat, w, h, intended_frames=n, integrator=integrator) as r:
         r.render_frames(0, n)
         assert np.allclose(r.read_accum(), bufs[0], rtol=1e-4, atol=1e-6)
+
+
+# --------------------------------------------------------------------------- BVH wavefront: queued shadow rays
+@pytest.mark.parametrize("math", [srt.MATH_EXACT, srt.MATH_FAST])
+def test_shadow_kernel_equals_in_place_shadow_rays(oracle, monkeypatch, math):
+    """Large BVH scenes trace their shadow rays in a kernel of their own (k_shade queues them per light, k_shadow
+    traces the queues in light order); the rays, their outcome and the terms are the same as with the rays traced in
+    place -- only the f32 association of several lights of one hit differs (per light instead of per pair)."""
+    sc = oracle.Scene(32, "spheres", 700)
+    flat = flat_from_oracle(sc)
+    w, h, n = 160, 90, 3
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SRT_SHADOW_KERNEL", flag)
+        with srt.Renderer(flat, w, h, intended_frames=8, math=math, integrator=srt.INTEGRATOR_WAVEFRONT, max_bounces=6) as r:
+            for f in range(n):           # one frame per call: a pixel's terms are added in path order
+                r.render_frames(f, 1)
+            out.append((r.read_accum(), r.counters()))
+    (a, ca), (b, cb) = out
+    for k in ("samples", "rays_primary", "rays_continuation", "rays_shadow", "shadow_skipped", "hits", "self_hits", "lit", "spec_hits",
+              "spec_dropped", "misses"):
+        assert ca[k] == cb[k], (k, ca[k], cb[k])
+    assert cb["kernel_launches"] > ca["kernel_launches"]          # (the queued rays really went through k_shadow)
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-9, equal_nan=True)
+    # deterministic: the same render twice gives the same bits
+    monkeypatch.setenv("SRT_SHADOW_KERNEL", "1")
+    with srt.Renderer(flat, w, h, intended_frames=8, math=math, integrator=srt.INTEGRATOR_WAVEFRONT, max_bounces=6) as r:
+        for f in range(n):
+            r.render_frames(f, 1)
+        assert np.array_equal(r.read_accum(), b, equal_nan=True)
