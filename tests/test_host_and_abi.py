@@ -173,3 +173,35 @@ def test_checkpoint_open_rejects_hostile_files_without_allocating(tmp_path, case
     rc = lib.srt_checkpoint_open(str(path).encode(), -1, C.byref(h))
     assert rc in (srt.native.SRT_ERR_INVALID_ARGUMENT, srt.native.SRT_ERR_UNSUPPORTED) and not h.value
     assert b"checkpoint" in lib.srt_last_error(None)
+
+
+def test_rust_binding_matches_header():
+    """ffi/src/lib.rs (the -sys side of the boundary; it cannot be compiled here -- no Rust toolchain) must declare
+    exactly the functions of include/srt.h, and mirror every struct field for field in the header's order."""
+    header = open(os.path.join(ROOT, "include", "srt.h")).read()
+    rust = open(os.path.join(ROOT, "ffi", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\b(srt_[a-z0-9_]+)\s*\(", header))
+    bound = set(re.findall(r"pub fn (srt_[a-z0-9_]+)\s*\(", rust))
+    assert declared == bound, (sorted(declared - bound), sorted(bound - declared))
+    for name in ("srt_object", "srt_material", "srt_light", "srt_camera", "srt_params", "srt_counters"):
+        c_body = re.search(r"typedef struct " + name + r" \{(.*?)\} " + name + ";", header, re.S).group(1)
+        c_body = re.sub(r"/\*.*?\*/", "", c_body, flags=re.S)
+        c_fields = []
+        for decl in c_body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ctype, names = decl.split(None, 1)
+            for n in names.split(","):
+                m = re.match(r"\s*([a-z0-9_]+)(?:\[(\d+)\])?", n)
+                c_fields.append((m.group(1), ctype, int(m.group(2) or 1)))
+        r_body = re.search(r"pub struct " + name + r" \{(.*?)\n    \}", rust, re.S).group(1)
+        r_fields = []
+        for m in re.finditer(r"pub ([a-z0-9_]+): (\[(\w+); (\d+)\]|\w+)", r_body):
+            r_fields.append((m.group(1), m.group(3) or m.group(2), int(m.group(4) or 1)))
+        tmap = {"float": "f32", "uint32_t": "u32", "int32_t": "i32", "uint64_t": "u64"}
+        assert [(n, tmap[t], k) for n, t, k in c_fields] == r_fields, name
+    # the status codes and enums carry the header's values
+    for cname, value in re.findall(r"(SRT_[A-Z0-9_]+) = (\d+)", header):
+        m = re.search(r"pub const " + cname + r": \w+ = (\d+);", rust)
+        assert m and int(m.group(1)) == int(value), cname
