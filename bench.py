@@ -392,11 +392,24 @@ def main():
                                         "term -- the mode whose samples equal the oracle's one by one" if key == "exact_math" else
                                         "SRT_RNG_PHILOX: Philox4x32-10 keyed (pixel, frame, bounce), the north star's RNG")}
 
+        # ---------------- every power-of-two spectral width (spectrum.rs:37-38 allows 8..=128), both integrators
+        extras["widths"] = {}
+        for nl in (8, 16, 32, 64, 128):
+            fl = scenes.preset(SCENE, nl)
+            row = {}
+            for name, integ in (("resident", 1), ("wavefront", 0)):
+                with srt.Renderer(fl, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=SPP_NAMED, integrator=integ, device=local_rank) as rr:
+                    t = timed_render(rr, 2, 1, 16, reduce=False)
+                    row[name] = t["samples"] / (t["ms"] * 1e-3)
+            extras["widths"][str(nl)] = row
+        extras["widths"]["what"] = ("samples/s of the 1080p Cornell box at n_lambda spectral samples (2 steps x 16 frames per rank, no reduce): the "
+                                    "resident integrator exists for every legal width, AUTO picks it for linear-scan scenes")
+
         # ---------------- BASELINE.json's other configs, every rank its shard of frames, reduce inside the clock
         cfgs = [("C0", "default scene 400x300, 64 iterations (the reference workload)", "default", 0, 400, 300, 64, 64, 4),
                 ("C2", "prism dispersion (extension) 1920x1080, 4096 spp", "prism", 0, 1920, 1080, 4096, 32, 3),
                 ("C3", "Cornell box 3840x2160, 16384 spp", "cornell", 0, 3840, 2160, 16384, 8, 3),
-                ("C4", "10 000 random spheres (BVH) 1920x1080, 1024 spp", "spheres", 10000, 1920, 1080, 1024, 16, 3)]
+                ("C4", "10 000 random spheres (BVH) 1920x1080, 1024 spp", "spheres", 10000, 1920, 1080, 1024, 32, 3)]
         extras["configs"] = {}
         for cid, desc, preset, arg, w, h, spp, frames, steps in cfgs:
             fl = scenes.preset(preset, N_LAMBDA, arg)
