@@ -502,8 +502,12 @@ void prof_collect(srt_ctx* c) {
     c->prof_used = 0;
 }
 
-void launch_iteration(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame) {
-    dim3 grid((c->capacity + kBlock - 1) / kBlock);
+// live_bound: an upper bound of the paths this iteration can hold -- the pool's capacity while samples are still being
+// generated, the last count the host has seen once they are not (the count only shrinks from then on).  The tail of a
+// render call is dozens of iterations over a handful of paths; covering the whole pool with blocks that exit at once
+// cost 5-10 us per kernel there.
+void launch_iteration(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame, uint32_t live_bound) {
+    dim3 grid(std::max(1u, (std::min(live_bound, c->capacity) + kBlock - 1) / kBlock));
     if (c->profiling) prof_event(c);
     k_generate<<<grid, kBlock, 0, c->stream>>>(c->scene, c->pool[parity], c->ctl, parity, c->capacity, total, first_frame,
                                               c->counters, c->shq.count);
@@ -981,6 +985,7 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
     uint32_t chunk = 8;
     unsigned long long goal = total;   // samples this call will generate (shrinks on abort)
     unsigned long long generated = 0;  // next_sample as of the last look at the control block
+    uint32_t live_bound = c->capacity; // see launch_iteration
     while (!done) {
         if (c->abort_flag && !aborted) {
             aborted = true;
@@ -989,7 +994,7 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
             if (goal == 0) break;  // nothing was started
         }
         for (uint32_t k = 0; k < chunk; ++k) {
-            launch_iteration(c, parity, goal, first_frame);
+            launch_iteration(c, parity, goal, first_frame, live_bound);
             parity ^= 1;
         }
         CUDA_TRY(c, cudaGetLastError());
@@ -998,6 +1003,7 @@ static int render_frames_impl(srt_ctx* c, uint32_t first_frame, uint32_t n_frame
         if (c->profiling) prof_collect(c);
         const PoolCtl& now = c->h_ctl[parity];
         generated = now.next_sample;
+        if (now.next_sample >= goal) live_bound = now.count;
         done = now.count == 0 && now.next_sample >= goal;
         if (!done) {
             // remaining work in pool-fills, to size the next chunk (at least the tail of
