@@ -434,22 +434,25 @@ void launch_shade_nl(srt_ctx* c, int parity, unsigned long long total, uint32_t 
     const PathPool& nxt = c->pool[parity ^ 1];
     float4* acc = reinterpret_cast<float4*>(c->accum);
     const ShadowQueue shq = Accel::kShadowKernel ? c->shq : ShadowQueue{};
-    if (c->scene.n_lambda4 == 8)
-        k_shade<Accel, EXACT, PHILOX, 8><<<grid, kBlock, 0, c->stream>>>(c->scene, cur, nxt, c->ctl, parity, c->capacity,
-                                                                        total, first_frame, c->hits, acc, c->counters, shq);
-    else
-        k_shade<Accel, EXACT, PHILOX, 0><<<grid, kBlock, 0, c->stream>>>(c->scene, cur, nxt, c->ctl, parity, c->capacity,
-                                                                        total, first_frame, c->hits, acc, c->counters, shq);
+#define SRT_SHADE(NL4, Q)                                                                                                     \
+    k_shade<Accel, EXACT, PHILOX, NL4, Q><<<grid, kBlock, 0, c->stream>>>(c->scene, cur, nxt, c->ctl, parity, c->capacity, total, \
+                                                                         first_frame, c->hits, acc, c->counters, shq)
     if (Accel::kShadowKernel && shq.count) {
+        if (c->scene.n_lambda4 == 8) SRT_SHADE(8, Accel::kShadowKernel);
+        else SRT_SHADE(0, Accel::kShadowKernel);
         // the queued shadow rays, one launch per light in light order (k_shadow)
         for (uint32_t l = 0; l < c->scene.n_lights; ++l) {
             if (c->scene.n_lambda4 == 8)
-                k_shadow<EXACT, 8><<<grid, kBlock, 0, c->stream>>>(c->scene, shq, l, c->capacity, nxt.thr, acc, c->counters);
+                k_shadow<EXACT, 8><<<grid, kBlock, 0, c->stream>>>(c->scene, shq, l, c->capacity, nxt.thr, cur.thr, acc, c->counters);
             else
-                k_shadow<EXACT, 0><<<grid, kBlock, 0, c->stream>>>(c->scene, shq, l, c->capacity, nxt.thr, acc, c->counters);
+                k_shadow<EXACT, 0><<<grid, kBlock, 0, c->stream>>>(c->scene, shq, l, c->capacity, nxt.thr, cur.thr, acc, c->counters);
         }
         c->launches += c->scene.n_lights;
+    } else {
+        if (c->scene.n_lambda4 == 8) SRT_SHADE(8, false);
+        else SRT_SHADE(0, false);
     }
+#undef SRT_SHADE
 }
 template <class Accel>
 void launch_shade(srt_ctx* c, int parity, unsigned long long total, uint32_t first_frame, dim3 grid) {
@@ -844,7 +847,7 @@ static int srt_create_body(const srt_params* params, const srt_camera* camera, c
     // per call: 2 Mi paths 1.10 G samples/s, 4 Mi 1.28 G, 8 Mi 1.31 G, 16 Mi 1.30 G, 32 Mi 1.15 G
     uint32_t cap = params->pool_paths ? params->pool_paths
                                       : (uint32_t)std::min<uint64_t>(1u << 23, std::max<uint64_t>(1u << 16, 4ull * sp.npix));
-    cap = std::max(cap, (uint32_t)kBlock);
+    cap = std::min(std::max(cap, (uint32_t)kBlock), 1u << 29);  // (the shadow queue keeps a slot index in 30 bits)
     cap = (cap + kBlock - 1) / kBlock * kBlock;
     c->capacity = cap;
     CREATE_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));

@@ -118,7 +118,8 @@ struct PathPool {
 
 // Shadow-ray queue of the BVH wavefront: one region of `capacity` records per light, filled by k_shade and traced by
 // k_shadow (srt_kernels.cuh).  a = origin.xyz, |L|; b = direction.xyz, pixel (bits); c = the light's factors
-// (production math: c1*c2/|L|^2, -, -; exact math: |L|^2, c1, c2) and the path's slot in the next pool | scrub << 31 (bits).
+// (production math: c1*c2/|L|^2, -, -; exact math: |L|^2, c1, c2) and the slot that holds the path's advanced throughput
+// (bits 0..29; bit 30: in the pool the path came from -- its last bounce -- instead of the next pool; bit 31: scrub).
 struct ShadowQueue {
     float4* a = nullptr;
     float4* b = nullptr;

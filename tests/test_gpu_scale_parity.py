@@ -237,8 +237,9 @@ def test_deterministic_mode_is_bit_reproducible(integrator):
 
 
 # --------------------------------------------------------------------------- BVH wavefront: queued shadow rays
+@pytest.mark.parametrize("max_bounces", [1, 6])          # 1: every hit is a path's last bounce (its throughput stays in its own pool)
 @pytest.mark.parametrize("math", [srt.MATH_EXACT, srt.MATH_FAST])
-def test_shadow_kernel_equals_in_place_shadow_rays(oracle, monkeypatch, math):
+def test_shadow_kernel_equals_in_place_shadow_rays(oracle, monkeypatch, math, max_bounces):
     """Large BVH scenes trace their shadow rays in a kernel of their own (k_shade queues them per light, k_shadow
     traces the queues in light order); the rays, their outcome and the terms are the same as with the rays traced in
     place -- only the f32 association of several lights of one hit differs (per light instead of per pair)."""
@@ -248,7 +249,7 @@ def test_shadow_kernel_equals_in_place_shadow_rays(oracle, monkeypatch, math):
     out = []
     for flag in ("0", "1"):
         monkeypatch.setenv("SRT_SHADOW_KERNEL", flag)
-        with srt.Renderer(flat, w, h, intended_frames=8, math=math, integrator=srt.INTEGRATOR_WAVEFRONT, max_bounces=6) as r:
+        with srt.Renderer(flat, w, h, intended_frames=8, math=math, integrator=srt.INTEGRATOR_WAVEFRONT, max_bounces=max_bounces) as r:
             for f in range(n):           # one frame per call: a pixel's terms are added in path order
                 r.render_frames(f, 1)
             out.append((r.read_accum(), r.counters()))
@@ -261,7 +262,7 @@ def test_shadow_kernel_equals_in_place_shadow_rays(oracle, monkeypatch, math):
     assert np.allclose(a, b, rtol=1e-5, atol=1e-9, equal_nan=True)
     # deterministic: the same render twice gives the same bits
     monkeypatch.setenv("SRT_SHADOW_KERNEL", "1")
-    with srt.Renderer(flat, w, h, intended_frames=8, math=math, integrator=srt.INTEGRATOR_WAVEFRONT, max_bounces=6) as r:
+    with srt.Renderer(flat, w, h, intended_frames=8, math=math, integrator=srt.INTEGRATOR_WAVEFRONT, max_bounces=max_bounces) as r:
         for f in range(n):
             r.render_frames(f, 1)
         assert np.array_equal(r.read_accum(), b, equal_nan=True)
