@@ -329,6 +329,7 @@ struct srt_ctx {
     DevObject* objects_g = nullptr;
     DevBvhNode* bvh_nodes = nullptr;
     uint32_t* bvh_prims = nullptr;
+    float4* bvh_leaf = nullptr;
     float4* frames = nullptr;  // SceneParams::frames
     uint64_t frames_accumulated = 0;
     uint64_t iterations = 0, launches = 0;
@@ -420,6 +421,7 @@ void free_ctx(srt_ctx* c) {
     cudaFree(c->objects_g);
     cudaFree(c->bvh_nodes);
     cudaFree(c->bvh_prims);
+    cudaFree(c->bvh_leaf);
     cudaFree(c->frames);
     for (cudaEvent_t e : c->prof_events) cudaEventDestroy(e);
     if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -736,9 +738,23 @@ static int srt_create_body(const srt_params* params, const srt_camera* camera, c
         CREATE_TRY(cudaMemcpy(c->bvh_nodes, nodes.data(), nodes.size() * sizeof(DevBvhNode), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMalloc(&c->bvh_prims, prim_index.size() * sizeof(uint32_t)));
         CREATE_TRY(cudaMemcpy(c->bvh_prims, prim_index.data(), prim_index.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        std::vector<float4> leaf(2 * prim_index.size());
+        for (size_t slot = 0; slot < prim_index.size(); ++slot) {
+            const DevObject& o = dev_objs[prim_index[slot]];
+            uint32_t idx = prim_index[slot];
+            float idx_bits;
+            std::memcpy(&idx_bits, &idx, 4);
+            float word_bits;
+            std::memcpy(&word_bits, &o.kind_orig, 4);
+            leaf[2 * slot] = make_float4(o.mn[0], o.mn[1], o.mn[2], word_bits);
+            leaf[2 * slot + 1] = make_float4(o.mx[0], o.mx[1], o.mx[2], idx_bits);
+        }
+        CREATE_TRY(cudaMalloc(&c->bvh_leaf, leaf.size() * sizeof(float4)));
+        CREATE_TRY(cudaMemcpy(c->bvh_leaf, leaf.data(), leaf.size() * sizeof(float4), cudaMemcpyHostToDevice));
         sp.objects_g = c->objects_g;
         sp.bvh_nodes = c->bvh_nodes;
         sp.bvh_prims = c->bvh_prims;
+        sp.bvh_leaf = c->bvh_leaf;
     } else {
         // index word of a linear-scan scene: (orig << 10) | (staged index << 2) | kind  (ClosestKey, srt_kernels.cuh)
         static_assert(kMaxConstObjects <= 256, "staged index field of the index word");

@@ -4,6 +4,8 @@
 #pragma once
 #include <cstdint>
 
+#include <cuda_runtime.h>
+
 namespace srt {
 
 constexpr int kMaxLambda = 128;        // spectrum.rs:8  NBR_OF_SAMPLES_MAX
@@ -84,6 +86,8 @@ struct SceneParams {
     const DevObject* objects_g;
     const DevBvhNode* bvh_nodes;
     const uint32_t* bvh_prims;              // primitive slot -> object index
+    const float4* bvh_leaf;                 // primitive slot -> (mn.xyz, kind_orig), (mx.xyz, object index): all a sphere or
+                                            // plain-box test needs, 32 contiguous bytes per primitive in leaf order
     // face_towards() of every box-face normal (k_build_frames): 3 float4 per frame; frames 0..5 = the axis
     // normals of plain boxes, 6 + 6*r + face = rotated box r (r < n_frame_rot)
     const float4* frames;
