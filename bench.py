@@ -409,7 +409,7 @@ def main():
         cfgs = [("C0", "default scene 400x300, 64 iterations (the reference workload)", "default", 0, 400, 300, 64, 64, 4),
                 ("C2", "prism dispersion (extension) 1920x1080, 4096 spp", "prism", 0, 1920, 1080, 4096, 32, 3),
                 ("C3", "Cornell box 3840x2160, 16384 spp", "cornell", 0, 3840, 2160, 16384, 8, 3),
-                ("C4", "10 000 random spheres (BVH) 1920x1080, 1024 spp", "spheres", 10000, 1920, 1080, 1024, 32, 3)]
+                ("C4", "10 000 random spheres (BVH) 1920x1080, 1024 spp", "spheres", 10000, 1920, 1080, 1024, 64, 3)]
         extras["configs"] = {}
         for cid, desc, preset, arg, w, h, spp, frames, steps in cfgs:
             fl = scenes.preset(preset, N_LAMBDA, arg)
@@ -436,18 +436,28 @@ def main():
                 rr.render_frames(first + done, n)
                 dev_ms += rr.last_render_stats()[0]
                 done += n
+            t_render = time.perf_counter() - t0
             if world > 1:
                 reduce_contexts_(rr, dst=0)
+            t_reduce = time.perf_counter() - t0
             if rank == 0:
                 assert rr.frames_accumulated == SPP_NAMED
                 rr.resolve_rgba_f32(host_np)
+            t_resolve = time.perf_counter() - t0
             barrier()
             strong_s = max_over_ranks(time.perf_counter() - t0)
+            phases = torch.tensor([t_render, t_reduce, t_resolve], dtype=torch.float64, device="cuda")
+            if world > 1:
+                gathered = [torch.zeros_like(phases) for _ in range(world)]
+                dist.all_gather(gathered, phases)
+            else:
+                gathered = [phases]
             extras["strong"] = {"what": f"{SPP_NAMED} spp of the 1080p Cornell box split over {world} rank(s): render in launches of <= {F} "
                                         "frames, NCCL reduce onto rank 0, resolve + read-back of the f32 image there; wall clock between "
                                         "barriers, max over ranks",
                                 "seconds": strong_s, "value": SPP_NAMED * npix / strong_s, "unit": "samples/s",
-                                "render_ms_max": max_over_ranks(dev_ms), "frames_per_rank": count}
+                                "render_ms_max": max_over_ranks(dev_ms), "frames_per_rank": count,
+                                "per_rank_s_after_render_reduce_resolve": [[round(float(v), 5) for v in g] for g in gathered]}
 
         # ---------------- srt_reduce (libsrt_nccl.so: one process, one context per device) against the torch path
         if world > 1:

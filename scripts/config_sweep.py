@@ -14,7 +14,7 @@ CONFIGS = [
     ("C1 Cornell box 1920x1080", "cornell", 0, 1920, 1080, 1024, 32),
     ("C2 prism (dispersion extension) 1920x1080", "prism", 0, 1920, 1080, 4096, 32),
     ("C3 Cornell box 3840x2160", "cornell", 0, 3840, 2160, 16384, 8),
-    ("C4 10k random spheres (BVH) 1920x1080", "spheres", 10000, 1920, 1080, 1024, 32),
+    ("C4 10k random spheres (BVH) 1920x1080", "spheres", 10000, 1920, 1080, 1024, 64),
 ]
 
 

@@ -858,11 +858,11 @@ static int srt_create_body(const srt_params* params, const srt_camera* camera, c
         }
     }
     // path pools + accumulation buffer
-    // default pool: four frames' worth of paths, at most 8 Mi (3.5 GB of path state with two shadow queues): the kernels
+    // default pool: eight frames' worth of paths, at most 16 Mi (7 GB of path state with two shadow queues): the kernels
     // of an iteration are latency-bound on their tails, so fewer and larger iterations win -- 10 000 spheres, 32 frames
-    // per call: 2 Mi paths 1.10 G samples/s, 4 Mi 1.28 G, 8 Mi 1.31 G, 16 Mi 1.30 G, 32 Mi 1.15 G
+    // per call: 2 Mi paths 1.10 G samples/s, 4 Mi 1.28 G, 8 Mi 1.31 G (later 1.42 G), 16 Mi 1.44 G, 32 Mi 1.15 G
     uint32_t cap = params->pool_paths ? params->pool_paths
-                                      : (uint32_t)std::min<uint64_t>(1u << 23, std::max<uint64_t>(1u << 16, 4ull * sp.npix));
+                                      : (uint32_t)std::min<uint64_t>(1u << 24, std::max<uint64_t>(1u << 16, 8ull * sp.npix));
     cap = std::min(std::max(cap, (uint32_t)kBlock), 1u << 29);  // (the shadow queue keeps a slot index in 30 bits)
     cap = (cap + kBlock - 1) / kBlock * kBlock;
     c->capacity = cap;
