@@ -361,6 +361,7 @@ def main():
         return False
 
     r.render_progressive(0, 1, 1, lambda *a: False, preview=True)  # (allocates the preview buffers / second stream: untimed)
+    r.resolve_rgba_f32(host_np)                                    # (... and the f32 resolve buffer)
     r.clear()
     seen.clear()
     barrier()
@@ -424,7 +425,9 @@ def main():
         # ---------------- the named config as a FIXED job: 1024 spp split over the ranks, reduce + resolve in the clock
         with srt.Renderer(flat, WIDTH, HEIGHT, max_bounces=BOUNCES, intended_frames=SPP_NAMED, integrator=args.integrator,
                           device=local_rank) as rr:
-            rr.render_frames(SPP_NAMED, 8)  # warm
+            rr.render_frames(SPP_NAMED, 8)  # warm (first launch, and the context's resolve buffer, outside the clock)
+            if rank == 0:
+                rr.resolve_rgba_f32(host_np)
             rr.clear()
             first, count = frame_shard(0, SPP_NAMED, rank, world)
             barrier()
