@@ -1,19 +1,28 @@
 // srt_headless.cpp -- command-line sibling of App::dispatch_render (main.rs:1376): renders a preset
-// without the eframe UI and writes the image (binary PPM, the RGBA8 conversion of
-// custom_image.rs:92-101 minus alpha) plus a one-line JSON summary.
+// without the eframe UI and writes the image -- the RGBA8 conversion of custom_image.rs:92-101, as a PNG
+// like the reference's "Save Image" does through DynamicImage::save (main.rs:2325-2326), or as a binary PPM
+// (RGB) when the name ends in .ppm -- plus a one-line JSON summary.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "srt_host.hpp"
 
 using namespace srt_host;
 
+namespace {
+bool ends_with(const std::string& s, const char* suffix) {
+    const size_t n = std::strlen(suffix);
+    return s.size() >= n && s.compare(s.size() - n, n, suffix) == 0;
+}
+}  // namespace
+
 static void usage() {
     std::fprintf(stderr,
                  "usage: srt_headless [--scene default|cornell|spheres|prism] [--spheres N] [--width W] [--height H]\n"
                  "                    [--spp N] [--bounces N] [--nlambda N] [--rng pcg3d|philox] [--math fast|exact]\n"
-                 "                    [--device D] [--out image.ppm]\n");
+                 "                    [--device D] [--out image.png | image.ppm]\n");
 }
 
 int main(int argc, char** argv) {
@@ -55,11 +64,16 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "\n");
         if (!out.empty()) {
             std::vector<uint8_t> px = r.image.to_rgba8();
-            FILE* f = std::fopen(out.c_str(), "wb");
-            if (!f) { std::perror("fopen"); return 1; }
-            std::fprintf(f, "P6\n%u %u\n255\n", ui.width, ui.height);
-            for (size_t i = 0; i < (size_t)ui.width * ui.height; ++i) std::fwrite(&px[4 * i], 1, 3, f);
-            std::fclose(f);
+            if (ends_with(out, ".ppm")) {
+                FILE* f = std::fopen(out.c_str(), "wb");
+                if (!f) { std::perror("fopen"); return 1; }
+                std::fprintf(f, "P6\n%u %u\n255\n", ui.width, ui.height);
+                for (size_t i = 0; i < (size_t)ui.width * ui.height; ++i) std::fwrite(&px[4 * i], 1, 3, f);
+                std::fclose(f);
+            } else if (!write_png_rgba8(out, ui.width, ui.height, px)) {
+                std::fprintf(stderr, "srt_headless: cannot write %s\n", out.c_str());
+                return 1;
+            }
         }
         const double samples = (double)r.counters.samples;
         const double rays = (double)(r.counters.rays_primary + r.counters.rays_continuation + r.counters.rays_shadow);

@@ -20,6 +20,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <algorithm>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -588,6 +590,87 @@ inline RaytracingUniforms build_uniforms(UIFields& ui) {
 }
 
 // ============================================================== custom_image.rs
+// A PNG writer without dependencies: 8-bit RGBA, filter 0, zlib stream of STORED deflate blocks (no compression --
+// every PNG reader accepts it).  CRC-32 over chunk type + data, Adler-32 over the raw scanlines (RFC 1950 / 1951 / 2083).
+inline uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (uint32_t i = 0; i < 256; ++i) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        ready = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+inline void put_be32(std::vector<uint8_t>& v, uint32_t x) {
+    for (int s = 24; s >= 0; s -= 8) v.push_back((uint8_t)(x >> s));
+}
+inline bool write_chunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    std::vector<uint8_t> head;
+    put_be32(head, (uint32_t)data.size());
+    head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32_update(0xffffffffu, reinterpret_cast<const uint8_t*>(type), 4);
+    crc = crc32_update(crc, data.data(), data.size()) ^ 0xffffffffu;
+    std::vector<uint8_t> tail;
+    put_be32(tail, crc);
+    return std::fwrite(head.data(), 1, head.size(), f) == head.size() &&
+           (data.empty() || std::fwrite(data.data(), 1, data.size(), f) == data.size()) &&
+           std::fwrite(tail.data(), 1, 4, f) == 4;
+}
+inline bool write_png_rgba8(const std::string& path, uint32_t w, uint32_t h, const std::vector<uint8_t>& rgba) {
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    bool ok = std::fwrite(sig, 1, 8, f) == 8;
+    std::vector<uint8_t> ihdr;
+    put_be32(ihdr, w);
+    put_be32(ihdr, h);
+    const uint8_t rest[5] = {8, 6, 0, 0, 0};  // bit depth 8, colour type 6 (RGBA), deflate, adaptive filtering, no interlace
+    ihdr.insert(ihdr.end(), rest, rest + 5);
+    ok = ok && write_chunk(f, "IHDR", ihdr);
+    // raw data: every scanline preceded by its filter byte (0 = none)
+    std::vector<uint8_t> raw;
+    raw.reserve((size_t)h * (4 * (size_t)w + 1));
+    for (uint32_t y = 0; y < h; ++y) {
+        raw.push_back(0);
+        raw.insert(raw.end(), rgba.begin() + (size_t)y * w * 4, rgba.begin() + (size_t)(y + 1) * w * 4);
+    }
+    uint32_t a = 1, b = 0;  // Adler-32
+    for (size_t i = 0; i < raw.size();) {
+        const size_t n = std::min<size_t>(5552, raw.size() - i);
+        for (size_t k = 0; k < n; ++k) {
+            a += raw[i + k];
+            b += a;
+        }
+        a %= 65521u;
+        b %= 65521u;
+        i += n;
+    }
+    std::vector<uint8_t> z;
+    z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78);
+    z.push_back(0x01);
+    for (size_t i = 0; i < raw.size() || i == 0;) {
+        const size_t n = std::min<size_t>(65535, raw.size() - i);
+        const bool last = i + n >= raw.size();
+        z.push_back(last ? 1 : 0);
+        z.push_back((uint8_t)(n & 0xff));
+        z.push_back((uint8_t)(n >> 8));
+        z.push_back((uint8_t)(~n & 0xff));
+        z.push_back((uint8_t)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + i, raw.begin() + i + n);
+        i += n;
+        if (last) break;
+    }
+    put_be32(z, (b << 16) | a);
+    ok = ok && write_chunk(f, "IDAT", z) && write_chunk(f, "IEND", {});
+    return (std::fclose(f) == 0) && ok;
+}
+
 struct CustomImage {  // custom_image.rs:9-22: RGBA f32, row-major, top-left origin
     uint32_t width = 0, height = 0;
     std::vector<float> data;

@@ -125,6 +125,20 @@ void srth_to_rgba8(const float* data, size_t n, uint8_t* out) {
     std::memcpy(out, v.data(), n);
 }
 
+// CustomImage -> DynamicImage -> save(path) (main.rs:2325-2326) for an image given as CustomImage.data: the RGBA8
+// conversion of custom_image.rs:92-101 written as a PNG.  Returns 0 on success.
+int srth_save_png(const char* path, uint32_t width, uint32_t height, const float* data) {
+    try {
+        CustomImage img;
+        img.width = width;
+        img.height = height;
+        img.data.assign(data, data + (size_t)width * height * 4);
+        return write_png_rgba8(path, width, height, img.to_rgba8()) ? 0 : 1;
+    } catch (...) {
+        return 1;
+    }
+}
+
 // dispatch_render_headless for a preset: the call a user of the reference makes when they press
 // "start render", minus the GUI.  image = width*height*4 f32 (CustomImage.data).
 int srth_dispatch_render(const char* preset, uint32_t arg, uint32_t width, uint32_t height, uint32_t n_lambda,

@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "libsrt_host.so")
 
 HOST_EXPORTS = ("srth_last_error", "srth_scene_preset", "srth_scene_free", "srth_scene_counts", "srth_scene_copy",
-                "srth_spectrum", "srth_black_body", "srth_to_rgba8", "srth_dispatch_render", "srth_render_protocol", "srth_spectrum_tool")
+                "srth_spectrum", "srth_black_body", "srth_to_rgba8", "srth_save_png", "srth_dispatch_render", "srth_render_protocol", "srth_spectrum_tool")
 
 _lib = None
 
@@ -40,6 +40,7 @@ def host_lib() -> C.CDLL:
     L.srth_black_body.argtypes = [C.c_double, C.c_double]
     L.srth_black_body.restype = C.c_double
     L.srth_to_rgba8.argtypes = [fp, C.c_size_t, C.POINTER(C.c_uint8)]
+    L.srth_save_png.argtypes = [C.c_char_p, u32, u32, fp]
     L.srth_dispatch_render.argtypes = [C.c_char_p, u32, u32, u32, u32, u32, u32, u32, u32, C.c_int32, u32, u32, fp,
                                        C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(N.SrtCounters)]
     L.srth_spectrum_tool.argtypes = [u32, fp, u32, u32, fp]
@@ -134,3 +135,11 @@ def host_spectrum_tool(op: str, intensities, n_new: int = 0):
     if L.srth_spectrum_tool(code, v.ctypes.data_as(fp), v.shape[0], n_new, out.ctypes.data_as(fp)) != 0:
         raise ValueError(L.srth_last_error().decode())
     return out[:n_new] if code == 0 else (out[0] if code == 1 else out[:v.shape[0]])
+
+
+def save_png(path: str, image: np.ndarray) -> None:
+    """DynamicImage::from(CustomImage).save(path) (main.rs:2325-2326) by the C++ host mirror: image = (H, W, 4) f32."""
+    img = np.ascontiguousarray(image, np.float32)
+    h, w = img.shape[:2]
+    if host_lib().srth_save_png(str(path).encode(), w, h, img.ctypes.data_as(C.POINTER(C.c_float))) != 0:
+        raise OSError(f"cannot write {path}")

@@ -76,3 +76,25 @@ def test_headless_c0_matches_cpu_reference_port(oracle, headless_c0):
     floor = rel_rmse(other[..., :3][ok], b)
     assert rel_rmse(a, b) <= 0.8 * floor, (rel_rmse(a, b), floor)
     assert abs(a.mean() - b.mean()) / b.mean() <= 5e-3
+
+
+def test_headless_writes_the_png_the_reference_saves(tmp_path):
+    """The reference's "Save Image" goes DynamicImage::from(CustomImage) -> .save(path) (main.rs:2325-2326,
+    custom_image.rs:92-101): 8-bit RGBA, alpha 255.  srt_headless writes that PNG itself (no image library); a PNG
+    reader must give back exactly the RGBA8 export of the same render."""
+    from PIL import Image
+    out = str(tmp_path / "cornell.png")
+    w, h, spp = 200, 120, 4
+    p = subprocess.run([BIN, "--scene", "cornell", "--width", str(w), "--height", str(h), "--spp", str(spp), "--out", out],
+                       capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    im = Image.open(out)
+    assert im.mode == "RGBA" and im.size == (w, h)
+    got = np.asarray(im)
+    with srt.Renderer(scenes.preset("cornell", 32), w, h, intended_frames=spp) as r:
+        r.set_deterministic(True)
+        r.render_frames(0, spp)
+        want = r.resolve_rgba_u8()
+    assert (got[..., 3] == 255).all()
+    diff = np.abs(got.astype(int) - want.astype(int))
+    assert diff.max() <= 1 and (diff != 0).mean() <= 1e-3

@@ -205,3 +205,20 @@ def test_rust_binding_matches_header():
     for cname, value in re.findall(r"(SRT_[A-Z0-9_]+) = (\d+)", header):
         m = re.search(r"pub const " + cname + r": \w+ = (\d+);", rust)
         assert m and int(m.group(1)) == int(value), cname
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (7, 5), (400, 300), (1920, 35)])   # (the last one: more than one 64 KB deflate block)
+def test_host_png_export_round_trips(tmp_path, oracle, w, h):
+    """The PNG the headless entry saves (no image library: stored-deflate zlib stream, CRC-32, Adler-32) read back by
+    an independent PNG decoder equals the reference's RGBA8 conversion (custom_image.rs:92-101: clamp, * 255, truncate,
+    NaN -> 0) of the same CustomImage data."""
+    from PIL import Image
+    rng = np.random.default_rng(w * 1000 + h)
+    img = rng.uniform(-0.2, 1.3, (h, w, 4)).astype(np.float32)
+    img[..., 3] = 1.0
+    img.reshape(-1)[::97] = np.nan
+    path = tmp_path / "x.png"
+    scenes.save_png(path, img)
+    im = Image.open(path)
+    assert im.mode == "RGBA" and im.size == (w, h)
+    assert np.array_equal(np.asarray(im), oracle.to_rgba8(img))
