@@ -20,7 +20,10 @@ CONFIGS = [
 
 def main():
     out = []
+    only = os.environ.get("SRT_SWEEP_ONLY")  # e.g. "C4" or "C0,C4"
     for name, preset, arg, w, h, spp, frames in CONFIGS:
+        if only and name.split()[0] not in only.split(","):
+            continue
         flat = scenes.preset(preset, 32, arg)
         with srt.Renderer(flat, w, h, intended_frames=spp) as r:
             r.render_frames(0, 2)

@@ -65,46 +65,36 @@ def spheres_10k(oracle):
     return oracle.Scene(32, "spheres", 10000)
 
 
-def test_bvh_10k_spheres_primary_ids_and_t_bit_exact(oracle, spheres_10k):
-    """10 001 objects: depth of the tree, the 64-entry traversal stack, leaves of up to 4 primitives and the padded
-    distance culling, against the linear scan over all objects with the stable lowest-index tie-break."""
-    sc = spheres_10k
-    w, h = 192, 108
-    with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=64) as r:
-        for frame, n in ((0, 1), (37, 64)):
-            want_ids, want_t, _ = sc.primary(w, h, frame=frame, intended_frames=n)
-            if n != 64:
-                with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=n) as r1:
-                    ids, t = r1.primary_ids(frame)
-            else:
-                ids, t = r.primary_ids(frame)
-            assert np.array_equal(ids, want_ids)
-            assert np.array_equal(t, want_t)
-            assert len(np.unique(ids)) > 1000      # the camera really sees thousands of different spheres
+# The same gate for BASELINE's config C4 in the mode it is benchmarked in: production math, BVH, queued shadow rays
+# (k_shade -> k_shadow), against the oracle's render through the reference's linear scan over all 10 001 objects
+# (tests/golden/make_converged_spheres.py: 160x90, 256 spp, pcg3d keys).
+SPHERES_REL_RMSE, SPHERES_MEAN = 0.03, 0.002
 
 
 @pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
-def test_bvh_10k_spheres_per_sample_spectra(oracle, spheres_10k, integrator):
-    """Whole paths (closest hits, shadow rays through the BVH's any-hit traversal, specular gates) sample for sample."""
-    O = oracle
-    sc = spheres_10k
-    w, h, N = 96, 54, 8
-    O.set_modes(O.MATH_CANONICAL, O.RNG_PCG3D)
-    with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=N, math=srt.MATH_EXACT, integrator=integrator) as r:
-        for frame in (0, 3):
-            O.counters_reset()
-            _, want = sc.render(w, h, 1, first_frame=frame, intended_frames=N, spectral=True, threads=0)
-            oc = O.counters()
-            r.clear()
-            r.reset_counters()
-            r.render_frames(frame, 1)
-            got = r.read_accum()
-            gc = r.counters()
-            assert gc["samples"] == oc["samples"] and gc["rays_primary"] == oc["rays_primary"]
-            assert np.array_equal(np.isnan(got), np.isnan(want))
-            tol = SAMPLE_RTOL * np.maximum(np.abs(want), np.nanmax(np.abs(want)) * 1e-6)
-            bad = (np.abs(got - want) > tol) & ~np.isnan(want)
-            assert bad.sum() == 0, f"{bad.sum()} of {bad.size} spectral samples differ"
+def test_converged_10k_spheres_256spp_production_math(oracle, spheres_10k, integrator):
+    g = np.load(os.path.join(GOLDEN, "converged_spheres10k_160x90_256spp.npz"))
+    w, h, spp = int(g["width"]), int(g["height"]), int(g["spp"])
+    want = g["rgb"]
+    oc = dict(zip([str(k) for k in g["counter_names"]], [int(v) for v in g["counter_values"]]))
+    assert int(g["n_spheres"]) == 10000 and int(g["n_lambda"]) == 32
+    with srt.Renderer(flat_from_oracle(spheres_10k), w, h, intended_frames=spp, max_bounces=int(g["max_bounces"]), integrator=integrator) as r:
+        r.render_frames(0, spp)
+        got = r.resolve_rgba_f32()[..., :3]
+        c = r.counters()
+    assert c["samples"] == w * h * spp == oc["samples"]
+    assert np.isfinite(got).all() and np.isfinite(want).all()
+    stats = {"rel_rmse": rel_rmse(got, want), "mean_ratio": float(got.mean(dtype=np.float64) / want.mean(dtype=np.float64))}
+    print("converged gate, 10 000 spheres:", stats)
+    assert stats["rel_rmse"] <= SPHERES_REL_RMSE, stats          # measured 0.010 (exact math: 0.005)
+    assert abs(stats["mean_ratio"] - 1.0) <= SPHERES_MEAN, stats  # measured 1.00004
+    # Half of this scene's materials are metals: the oracle's recursion also traces -- and counts -- the subtree of a
+    # specular child that its parent then discards (shader.rs:407), the loop here stops at the discard.  So only the
+    # primaries are equal, everything else is bounded by the oracle's count (see test_continuation_rays_match_oracle_loop).
+    assert c["rays_primary"] == oc["rays_primary"]
+    for k in ("rays_continuation", "hits", "self_hits", "spec_hits", "spec_dropped"):
+        assert (0.4 if k == "spec_dropped" else 0.8) * oc[k] <= c[k] <= oc[k], (k, c[k], oc[k])   # measured 0.54 / 0.86 .. 0.96
+    assert c["rays_shadow"] + c["shadow_skipped"] <= oc["rays_shadow"]
 
 
 # --------------------------------------------------------------------------- every legal spectral width
