@@ -97,6 +97,48 @@ def test_converged_10k_spheres_256spp_production_math(oracle, spheres_10k, integ
     assert c["rays_shadow"] + c["shadow_skipped"] <= oc["rays_shadow"]
 
 
+def test_bvh_10k_spheres_primary_ids_and_t_bit_exact(oracle, spheres_10k):
+    """10 001 objects: depth of the tree, the 64-entry traversal stack, leaves of up to 4 primitives and the padded
+    distance culling, against the linear scan over all objects with the stable lowest-index tie-break."""
+    sc = spheres_10k
+    w, h = 192, 108
+    with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=64) as r:
+        for frame, n in ((0, 1), (37, 64)):
+            want_ids, want_t, _ = sc.primary(w, h, frame=frame, intended_frames=n)
+            if n != 64:
+                with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=n) as r1:
+                    ids, t = r1.primary_ids(frame)
+            else:
+                ids, t = r.primary_ids(frame)
+            assert np.array_equal(ids, want_ids)
+            assert np.array_equal(t, want_t)
+            assert len(np.unique(ids)) > 1000      # the camera really sees thousands of different spheres
+
+
+@pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
+def test_bvh_10k_spheres_per_sample_spectra(oracle, spheres_10k, integrator):
+    """Whole paths (closest hits, shadow rays through the BVH's any-hit traversal, specular gates) sample for sample."""
+    O = oracle
+    sc = spheres_10k
+    w, h, N = 96, 54, 8
+    O.set_modes(O.MATH_CANONICAL, O.RNG_PCG3D)
+    with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=N, math=srt.MATH_EXACT, integrator=integrator) as r:
+        for frame in (0, 3):
+            O.counters_reset()
+            _, want = sc.render(w, h, 1, first_frame=frame, intended_frames=N, spectral=True, threads=0)
+            oc = O.counters()
+            r.clear()
+            r.reset_counters()
+            r.render_frames(frame, 1)
+            got = r.read_accum()
+            gc = r.counters()
+            assert gc["samples"] == oc["samples"] and gc["rays_primary"] == oc["rays_primary"]
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            tol = SAMPLE_RTOL * np.maximum(np.abs(want), np.nanmax(np.abs(want)) * 1e-6)
+            bad = (np.abs(got - want) > tol) & ~np.isnan(want)
+            assert bad.sum() == 0, f"{bad.sum()} of {bad.size} spectral samples differ"
+
+
 # --------------------------------------------------------------------------- every legal spectral width
 @pytest.mark.parametrize("integrator", [srt.INTEGRATOR_WAVEFRONT, srt.INTEGRATOR_RESIDENT])
 @pytest.mark.parametrize("name,n_lambda", [("cornell", 8), ("cornell", 16), ("cornell", 24), ("cornell", 40), ("cornell", 64),
