@@ -298,3 +298,41 @@ def test_shadow_kernel_equals_in_place_shadow_rays(oracle, monkeypatch, math, ma
         for f in range(n):
             r.render_frames(f, 1)
         assert np.array_equal(r.read_accum(), b, equal_nan=True)
+
+
+# --------------------------------------------------------------------------- C4 at BASELINE's resolution: properties
+def test_c4_full_hd_properties(oracle, spheres_10k):
+    """10 000 spheres at 1920x1080 (the size the bench's `configs.C4` runs at), production math, the integrator AUTO
+    picks (wavefront: BVH, shadow-ray queues, k_shadow): the image and every event counter are independent of how the
+    frame range is split into calls and of the size of the path pool (64 Ki paths: hundreds of refill iterations per
+    frame instead of one), and the deterministic mode is bit-reproducible."""
+    flat = flat_from_oracle(spheres_10k)
+    w, h, n = 1920, 1080, 4
+    keys = ("samples", "rays_primary", "rays_continuation", "rays_shadow", "shadow_skipped", "hits", "self_hits", "misses", "lit",
+            "spec_hits", "spec_dropped")
+    runs = []
+    for pool, split in ((0, (4,)), (0, (1, 3)), (1 << 16, (2, 2))):
+        with srt.Renderer(flat, w, h, intended_frames=1024, pool_paths=pool) as r:
+            first = 0
+            for k in split:
+                r.render_frames(first, k)
+                first += k
+            assert r.frames_accumulated == n
+            runs.append((r.resolve_rgba_f32(), r.counters(), r.read_accum()))
+    img0, c0, acc0 = runs[0]
+    assert c0["samples"] == n * w * h == c0["rays_primary"]
+    assert np.isfinite(img0).all() and 0.01 < img0[..., :3].mean() < 2.0
+    for img, c, acc in runs[1:]:
+        for k in keys:
+            assert c[k] == c0[k], (k, c[k], c0[k])
+        # the same non-negative radiance terms added in another order: compared where nothing cancels, in the spectra
+        # (the XYZ -> RGB matrix has negative entries; saturated colours amplify an ulp of the spectrum in one channel)
+        assert np.allclose(acc, acc0, rtol=1e-5, atol=1e-7 * float(np.nanmax(acc0)), equal_nan=True)
+        assert np.abs(img - img0).max() <= 1e-4 * max(1.0, float(img0.max()))
+    bits = []
+    for _ in range(2):
+        with srt.Renderer(flat, w, h, intended_frames=1024) as r:
+            r.set_deterministic(True)
+            r.render_frames(0, 2)
+            bits.append(r.read_accum())
+    assert np.array_equal(bits[0], bits[1], equal_nan=True)
