@@ -830,15 +830,19 @@ static int srt_create_body(const srt_params* params, const srt_camera* camera, c
             const bool exact = params->math_mode == SRT_MATH_EXACT, philox = params->rng_mode == SRT_RNG_PHILOX;
             const int cap = nl4 <= 2 ? 2 : nl4 <= 4 ? 4 : nl4 <= 8 ? 8 : nl4 <= 16 ? 16 : 32;
             const bool partial = (uint32_t)cap != nl4;
+            // (one light: the diffuse-only kernels have a pair mode, see k_resident; SRT_RESIDENT_PAIR=0: developer override)
+            bool pair_mode = n_lights == 1;
+            if (const char* e = std::getenv("SRT_RESIDENT_PAIR")) pair_mode = pair_mode && std::atoi(e) != 0;
+            const int need = c->features | (pair_mode ? kFeatPair : 0);
             ResidentKernel k;
             switch (cap) {
 #ifndef SRT_DEV_ONLY_NL8
-            case 2: k = resident_kernel_nl2(c->use_bvh, exact, philox, c->features, partial); break;
-            case 4: k = resident_kernel_nl4(c->use_bvh, exact, philox, c->features, partial); break;
-            case 16: k = resident_kernel_nl16(c->use_bvh, exact, philox, c->features, partial); break;
-            case 32: k = resident_kernel_nl32(c->use_bvh, exact, philox, c->features, partial); break;
+            case 2: k = resident_kernel_nl2(c->use_bvh, exact, philox, need, partial); break;
+            case 4: k = resident_kernel_nl4(c->use_bvh, exact, philox, need, partial); break;
+            case 16: k = resident_kernel_nl16(c->use_bvh, exact, philox, need, partial); break;
+            case 32: k = resident_kernel_nl32(c->use_bvh, exact, philox, need, partial); break;
 #endif
-            case 8: k = resident_kernel_nl8(c->use_bvh, exact, philox, c->features, partial); break;
+            case 8: k = resident_kernel_nl8(c->use_bvh, exact, philox, need, partial); break;
             default: break;
             }
             if (k.fn) {

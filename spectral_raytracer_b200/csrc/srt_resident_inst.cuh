@@ -2,7 +2,7 @@
 // SRT_RESIDENT_FN (the selector's name): instantiates k_resident for that spectral capacity and defines the selector.
 //
 // Instantiations per capacity: production / exact math x pcg3d / Philox; linear scan: Cornell-like (diffuse, plain +
-// rotated boxes), [default-like (specular + spheres): the default width only], everything; BVH: everything, the
+// rotated boxes) and its pair mode for one-light scenes, [default-like (specular + spheres): the default width only], everything; BVH: everything, the
 // default width only (BVH scenes run the wavefront unless the resident integrator is asked for).  Partial widths
 // (capacity > n_lambda4) exist for the capacities that have widths below them: 8 (24), 16 (40..56), 32 (72..120).
 #define SRT_KERNELS_RESIDENT_ONLY 1
@@ -16,7 +16,7 @@ template <class Accel, int NL4, int FEAT>
 ResidentKernel pick_mode(bool exact, bool philox) {
     ResidentKernel k;
     k.cap = nl4_cap(NL4);
-    k.min_blocks = resident_min_blocks(nl4_cap(NL4));
+    k.min_blocks = resident_min_blocks(nl4_cap(NL4), (FEAT & kFeatPair) != 0);
     k.feat = FEAT;
 #ifdef SRT_DEV_MINIMAL  // developer builds for kernel A/B runs: production mode only (compiles in seconds)
     (void)exact; (void)philox;
@@ -40,7 +40,12 @@ ResidentKernel pick(bool bvh, bool exact, bool philox, int need) {
         return ResidentKernel{};
     }
     // the smallest instantiated superset of what the scene contains
-    if ((need & ~kCornellLike) == 0) return pick_mode<AccelLinear, NL4, kCornellLike>(exact, philox);
+    const bool one_light = (need & kFeatPair) != 0;  // (set by srt_create; not a lobe)
+    need &= kFeatAll;
+    if ((need & ~kCornellLike) == 0) {
+        if (one_light) return pick_mode<AccelLinear, NL4, kCornellLike | kFeatPair>(exact, philox);  // pair mode, see k_resident
+        return pick_mode<AccelLinear, NL4, kCornellLike>(exact, philox);
+    }
     if constexpr (kDefaultWidth)
         if ((need & ~kDefaultLike) == 0) return pick_mode<AccelLinear, NL4, kDefaultLike>(exact, philox);
     return pick_mode<AccelLinear, NL4, kFeatAll>(exact, philox);
