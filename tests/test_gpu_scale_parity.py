@@ -336,3 +336,49 @@ def test_c4_full_hd_properties(oracle, spheres_10k):
             r.render_frames(0, 2)
             bits.append(r.read_accum())
     assert np.array_equal(bits[0], bits[1], equal_nan=True)
+
+
+# --------------------------------------------------------------------------- resident kernel, pair mode
+@pytest.mark.parametrize("max_bounces", [1, 2, 3, 30])
+@pytest.mark.parametrize("w,h", [(5, 3), (64, 48)])
+def test_pair_mode_edges_sample_exact(oracle, w, h, max_bounces):
+    """One-light diffuse scenes run the resident kernel's pair mode (a lane's shadow ray and its next path ray share a
+    scan; the last shadow ray of a path rides along with the next sample's primary ray).  Paths of 1..3 bounces -- every
+    hit the path's last -- and images smaller than a warp, sample for sample and event for event against the oracle."""
+    O = oracle
+    sc = O.Scene(32, "cornell")
+    O.set_modes(O.MATH_CANONICAL, O.RNG_PCG3D)
+    with srt.Renderer(flat_from_oracle(sc), w, h, intended_frames=8, math=srt.MATH_EXACT, integrator=srt.INTEGRATOR_RESIDENT,
+                      max_bounces=max_bounces) as r:
+        for frame in (0, 5):
+            O.counters_reset()
+            _, want = sc.render(w, h, 1, first_frame=frame, intended_frames=8, spectral=True, threads=4, max_bounces=max_bounces)
+            oc = O.counters()
+            r.clear()
+            r.reset_counters()
+            r.render_frames(frame, 1)
+            got = r.read_accum()
+            gc = r.counters()
+            for k in ("samples", "rays_primary", "rays_continuation", "hits", "self_hits"):
+                assert gc[k] == oc[k], (k, gc[k], oc[k])
+            assert gc["rays_shadow"] + gc["shadow_skipped"] == oc["rays_shadow"]
+            assert np.array_equal(np.isnan(got), np.isnan(want))
+            tol = SAMPLE_RTOL * np.maximum(np.abs(want), np.nanmax(np.abs(want)) * 1e-6)
+            assert ((np.abs(got - want) > tol) & ~np.isnan(want)).sum() == 0
+
+
+def test_pair_mode_equals_pass_loop(monkeypatch):
+    """The same render through the pass-loop kernel (SRT_RESIDENT_PAIR=0, read by srt_create) and the pair-mode kernel:
+    the same paths -- every event counter equal -- and the same radiance terms, added in another order."""
+    flat = scenes.preset("cornell", 32)
+    w, h, n = 640, 360, 6
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SRT_RESIDENT_PAIR", flag)
+        with srt.Renderer(flat, w, h, intended_frames=64, integrator=srt.INTEGRATOR_RESIDENT) as r:
+            r.render_frames(3, n)
+            out.append((r.read_accum(), r.counters()))
+    (a, ca), (b, cb) = out
+    for k in ("samples", "rays_primary", "rays_continuation", "rays_shadow", "shadow_skipped", "hits", "self_hits", "misses", "lit"):
+        assert ca[k] == cb[k], (k, ca[k], cb[k])
+    assert np.allclose(a, b, rtol=1e-5, atol=1e-7 * float(np.nanmax(a)), equal_nan=True)
