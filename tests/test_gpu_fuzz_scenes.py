@@ -134,3 +134,57 @@ def test_ties_go_to_the_lowest_original_index(oracle, order):
             tol = SAMPLE_RTOL * np.maximum(np.abs(want), max(np.nanmax(np.abs(want)), 1e-30) * 1e-6)
             bad = (np.abs(got - want) > tol) & ~(np.isnan(got) & np.isnan(want))
             assert bad.sum() == 0, (order, accel, integrator, int(bad.sum()))
+
+
+def random_box_room(O, seed: int, n_lambda: int):
+    """Diffuse boxes only (plain and rotated, overlapping, some of them walls) and exactly ONE light: the scenes the
+    resident kernel runs in pair mode.  Emission up to 1e20 and reflectances up to 1 so that both accumulate variants
+    (tame scene or not) and the last-bounce hand-over are exercised."""
+    rng = np.random.default_rng(seed)
+    sc = O.Scene(n_lambda)
+    v = rng.normal(size=3)
+    eye = v / np.linalg.norm(v) * rng.uniform(1.5, 3.0)
+    if seed % 3 == 0:
+        eye = rng.uniform(-0.3, 0.3, 3)  # inside the cluster
+    sc.set_camera(eye, rng.uniform(-0.4, 0.4, 3) - eye, (0.0, 1.0, 0.0), float(rng.uniform(35.0, 95.0)))
+    refl = [sc.add_spectrum(rng.uniform(0.0, 1.0, n_lambda).astype(np.float32)) for _ in range(4)]
+    mats = [sc.add_material(0.0, float(rng.choice([0.0, 0.3])), int(rng.choice(refl))) for _ in range(4)]
+    for _ in range(int(rng.integers(1, 9))):
+        c, l, m = rng.uniform(-1.2, 1.2, 3), rng.uniform(0.1, 1.5, 3), int(rng.choice(mats))
+        if rng.integers(0, 2):
+            sc.add_box(c, l, m)
+        else:
+            sc.add_rotated_box(c, l, rng.uniform(-3.2, 3.2, 3), m)
+    if seed % 2 == 0:  # a closed room: nothing escapes, every path runs into the bounce limit
+        for c, l in (((0, -2.5, 0), (6, 0.2, 6)), ((0, 2.5, 0), (6, 0.2, 6)), ((-2.5, 0, 0), (0.2, 6, 6)), ((2.5, 0, 0), (0.2, 6, 6)),
+                     ((0, 0, -2.5), (6, 6, 0.2)), ((0, 0, 2.5), (6, 6, 0.2))):
+            sc.add_box(c, l, int(rng.choice(mats)))
+    scale = float(rng.choice([0.5, 30.0, 1e20]))
+    sc.add_light(rng.uniform(-2.0, 2.0, 3), sc.add_spectrum((rng.uniform(0.0, 1.0, n_lambda) * scale).astype(np.float32)))
+    return sc
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_one_light_box_rooms_pair_mode(oracle, seed):
+    O = oracle
+    n_lambda = (32, 8, 24, 64, 32, 128, 16, 40)[seed % 8]
+    max_bounces = (30, 4, 1, 7)[seed % 4]
+    rng_mode = 1 if seed % 5 == 2 else 0
+    w, h, N = 64, 48, 8
+    sc = random_box_room(O, 7000 + seed, n_lambda)
+    flat = flat_from_oracle(sc)
+    O.set_modes(O.MATH_CANONICAL, rng_mode, (9, seed))
+    try:
+        frames = (0, 6)
+        want = [sc.render(w, h, 1, first_frame=f, intended_frames=N, spectral=True, threads=4, max_bounces=max_bounces)[1] for f in frames]
+    finally:
+        O.set_modes(O.MATH_NATIVE, O.RNG_PCG3D)
+    with srt.Renderer(flat, w, h, intended_frames=N, math=srt.MATH_EXACT, rng=rng_mode, philox_seed=(9, seed), max_bounces=max_bounces,
+                      integrator=srt.INTEGRATOR_RESIDENT) as r:
+        for f, wnt in zip(frames, want):
+            got = _one_frame(r, f)
+            assert np.array_equal(np.isnan(got), np.isnan(wnt)), (seed, f)
+            both_nan = np.isnan(got) & np.isnan(wnt)
+            tol = SAMPLE_RTOL * np.maximum(np.abs(wnt), max(np.nanmax(np.abs(wnt)), 1e-30) * 1e-6)
+            bad = (np.abs(got - wnt) > tol) & ~both_nan
+            assert bad.sum() == 0, (seed, f, int(bad.sum()), bad.size)
