@@ -17,7 +17,7 @@ template <class Accel, int NL4, int FEAT>
 ResidentKernel pick_mode(bool exact, bool philox) {
     ResidentKernel k;
     k.cap = nl4_cap(NL4);
-    k.min_blocks = resident_min_blocks(nl4_cap(NL4), (FEAT & kFeatPair) != 0);
+    k.min_blocks = resident_min_blocks(nl4_cap(NL4), (FEAT & kFeatPair) != 0, (FEAT & (kFeatSpecular | kFeatTransmissive)) != 0);
     k.feat = FEAT;
 #ifdef SRT_DEV_MINIMAL  // developer builds for kernel A/B runs: production mode only (compiles in seconds)
     (void)exact; (void)philox;
